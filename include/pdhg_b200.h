@@ -1,0 +1,138 @@
+/* pdhg_b200.h — C ABI of the B200-native PDHG hot path.
+ *
+ * Drop-in boundary for the PDHG iteration of TingweiMeng/PDHG-optimal-control (reference paths are
+ * relative to /root/reference).  The reference has no FFI of its own (it is pure Python/JAX); the
+ * injection point this library replaces is the pair of callables + the solver loop they are passed to:
+ *
+ *   fn_update_primal / fn_update_dual        jaxsrc/run_example.py:193-203
+ *   PDHG_solver_oneiter(...)                 jaxsrc/utils/utils_pdhg_solver.py:9-94
+ *   PDHG_multi_step(...)                     jaxsrc/utils/utils_pdhg_solver.py:97-225
+ *
+ * The Python host package `pdhg_b200` binds these entry points with ctypes and re-exports the reference's
+ * names (`solve_HJ`, `PDHG_multi_step`, `PDHG_solver_oneiter`, `update_primal_1d/2d`,
+ * `update_dual_alternative`), see INTEGRATION.md.
+ *
+ * Conventions
+ *   - all arrays are C-contiguous fp64, t slowest, then x, then y, then control component — exactly the
+ *     reference's layouts with a leading batch axis B of independent problem instances:
+ *         phi [B][K+1][nx][ny]   rho [B][K][nx][ny]   alp [B][2*ndim][K][nx][ny][n_ctrl]
+ *         phi_all [B][nt][nx][ny]  rho_all [B][nt-1][nx][ny]  alp_all [B][2*ndim][nt-1][nx][ny][n_ctrl]
+ *     (ny = 1 in 1-D; K = time_step_per_PDHG - 1; nt = nblocks*K + 1);
+ *   - "dev" pointers are device pointers on the handle's GPU, "host" pointers are ordinary host memory;
+ *   - the caller owns every buffer; inputs are never modified; the handle owns its workspaces;
+ *   - every entry returns 0 on success or a negative pdhg_status; pdhg_last_error() gives the text.
+ *     No C++ exception crosses this boundary.  There is NO CPU fallback: without a CUDA device every
+ *     compute entry fails with PDHG_ERR_CUDA.
+ *   - a handle is bound to one device and is not thread-safe; `stream` is a cudaStream_t (NULL = default).
+ */
+#ifndef PDHG_B200_H_
+#define PDHG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pdhg_handle pdhg_handle;
+
+enum pdhg_status {
+  PDHG_OK = 0,
+  PDHG_ERR_ARG = -1,        /* invalid argument / unsupported configuration */
+  PDHG_ERR_CUDA = -2,       /* CUDA runtime error (incl. no device) */
+  PDHG_ERR_NOMEM = -3,
+  PDHG_ERR_UNSUPPORTED = -4 /* valid reference configuration this build does not cover */
+};
+
+/* per-instance result of a solve (pdhg_logs.status) */
+enum pdhg_inst_status {
+  PDHG_INST_OK = 0,
+  PDHG_INST_SOL_NAN = 1,      /* step-size fallback exhausted: "algorithm failed" (utils_pdhg_solver.py:184-187) */
+  PDHG_INST_PAUSED = 3,       /* stopped at iter_pause; resume with iter_begin = iters */
+  PDHG_INST_LOG_OVERFLOW = 4  /* more than max_rec-1 periodic records in one block; extra rows dropped */
+};
+
+/* how a time block ended (pdhg_logs.end_reason) */
+enum pdhg_end_reason { PDHG_END_CONVERGED = 0, PDHG_END_NAN = 1, PDHG_END_MAXITER = 2, PDHG_END_PAUSED = 3 };
+
+/* Static description of a problem family; replaces the closure state of run_example.py:157-203 and the
+ * `fns_dict` namedtuple of set_fns.py:164-166 (the callables cannot cross a C ABI: `egno` selects the
+ * compiled-in problem, `coef_x/coef_y` carry its coefficient tables). */
+typedef struct pdhg_config {
+  int32_t ndim;            /* 1 | 2 */
+  int32_t egno;            /* 1 quadratic L, 2 indicator L, 3 Newton (2-D only)      set_fns.py:52-166 */
+  int32_t nx, ny;          /* ny = 1 in 1-D */
+  int32_t K;               /* time_step_per_PDHG - 1 */
+  int32_t n_ctrl;          /* 1 (1-D, egno 3) | 2 (2-D egno 1,2)                     run_example.py:228-240 */
+  int32_t bc_x, bc_y;      /* 0 periodic, 1 Neumann                                   utils_diff_op.py:5-7 */
+  double dt, dx, dy;       /* run_example.py:160-162 */
+  double c_on_rho;         /* FLAGS.c_on_rho */
+  double C, pow, Ct;       /* preconditioner constants (pow, Ct ignored in 2-D)       utils_precond.py:105,142 */
+  double eps;              /* stopping tolerance, also the inner tolerance            utils_pdhg_solver.py:52,57 */
+  int32_t rho_alp_iters;   /* 10                                                      update_fns_in_pdhg.py:168 */
+  int32_t batch;           /* B: independent instances solved per call */
+  int32_t nblocks;         /* nt_PDHG = (nt-1)/K time blocks (1 for a single block solve) */
+  int32_t max_rec;         /* rows reserved per block in the error log (>= 2) */
+  int32_t device;          /* CUDA device ordinal */
+  int32_t path;            /* 0 auto | 1 single-CTA shared-memory kernel | 2 cooperative multi-CTA kernel */
+} pdhg_config;
+
+/* Host-side logs of a solve; any pointer may be NULL.  Shapes: [B][nblocks] unless noted. */
+typedef struct pdhg_logs {
+  int64_t* iters;          /* pdhg_iters of each accepted block (utils_pdhg_solver.py:91,189) */
+  double* stepsz_used;     /* stepsz_param each block was accepted with */
+  int32_t* nrec;           /* rows of errlog written for the block */
+  double* errlog;          /* [B][nblocks][max_rec][4]: err1, err2, min rho, max rho (= error_all rows) */
+  int32_t* end_reason;     /* pdhg_end_reason */
+  int32_t* status;         /* [B] pdhg_inst_status */
+  int32_t* blocks_done;    /* [B] number of accepted blocks */
+  double* stepsz_final;    /* [B] step size after the last fallback */
+  int64_t* inner_total;    /* [B] dual sweeps executed (statistics, not in the reference) */
+} pdhg_logs;
+
+/* coef_x[nx], coef_y[ny] (host): a(x)=(x-1)^2+0.1 per direction for egno 1,2 (set_fns.py:117-118,145);
+ * for egno 3 coef_x = the x grid itself (f_y = x, set_fns.py:98).  coef_y may be NULL in 1-D. */
+int pdhg_create(const pdhg_config* cfg, const double* coef_x, const double* coef_y, pdhg_handle** out);
+void pdhg_destroy(pdhg_handle* h);
+const char* pdhg_last_error(void);
+/* 1 = single-CTA kernel, 2 = cooperative kernel (what `path = 0` resolved to) */
+int pdhg_path(const pdhg_handle* h);
+/* number of kernel launches issued through this handle so far */
+int64_t pdhg_launch_count(const pdhg_handle* h);
+
+/* fn_update_primal (run_example.py:193-195,199-201 -> update_fns_in_pdhg.py:135-147), batch = 1 per call slot b.
+ * dev buffers: phi_prev/phi_next [B][K+1][n], rho_prev [B][K][n], alp_prev [B][2 ndim][K][n][n_ctrl]. */
+int pdhg_update_primal(pdhg_handle* h, const double* phi_prev_dev, const double* rho_prev_dev,
+                       const double* alp_prev_dev, const double* epsl_host, double tau,
+                       double* phi_next_dev, void* stream);
+
+/* fn_update_dual (run_example.py:196-197,202-203 -> update_fns_in_pdhg.py:167-180); n_inner_host[B] receives
+ * the number of sweeps executed. */
+int pdhg_update_dual(pdhg_handle* h, const double* phi_bar_dev, const double* rho_prev_dev,
+                     const double* alp_prev_dev, const double* epsl_host, double sigma, double eps,
+                     double* rho_next_dev, double* alp_next_dev, int32_t* n_inner_host, void* stream);
+
+/* PDHG_solver_oneiter (utils_pdhg_solver.py:9-94) for B instances: iterations [iter_begin, ...) of ONE time
+ * block from (phi0, rho0, alp0) with step size stepsz_host[b], until convergence / NaN / n_maxiter /
+ * iter_pause.  Final iterate -> *_out (may alias nothing).  logs use nblocks = 1. Synchronises the stream. */
+int pdhg_solve_block(pdhg_handle* h, const double* phi0_dev, const double* rho0_dev, const double* alp0_dev,
+                     const double* epsl_host, const double* stepsz_host, int64_t n_maxiter, int64_t iter_begin,
+                     int64_t iter_pause, int32_t print_freq, double* phi_out_dev, double* rho_out_dev,
+                     double* alp_out_dev, pdhg_logs* logs, void* stream);
+
+/* PDHG_multi_step (utils_pdhg_solver.py:97-225) for B instances: nblocks sequential time blocks from the
+ * initial data g [B][n] (phi0 = tile(g), rho0 = c_on_rho, alp0 = 0), with warm starts and the NaN step-size
+ * fallback.  stepsz_host[b] = initial stepsz_param.  Synchronises the stream. */
+int pdhg_multi_step(pdhg_handle* h, const double* g_dev, const double* epsl_host, const double* stepsz_host,
+                    int64_t n_maxiter, int32_t print_freq, double* phi_all_dev, double* rho_all_dev,
+                    double* alp_all_dev, pdhg_logs* logs, void* stream);
+
+/* Same as pdhg_multi_step with HOST buffers for g and the three outputs (H2D / D2H copies inside). */
+int pdhg_multi_step_host(pdhg_handle* h, const double* g_host, const double* epsl_host, const double* stepsz_host,
+                         int64_t n_maxiter, int32_t print_freq, double* phi_all_host, double* rho_all_host,
+                         double* alp_all_host, pdhg_logs* logs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDHG_B200_H_ */
