@@ -107,10 +107,12 @@ int pdhg_update_primal(pdhg_handle* h, const double* phi_prev_dev, const double*
                        double* phi_next_dev, void* stream);
 
 /* fn_update_dual (run_example.py:196-197,202-203 -> update_fns_in_pdhg.py:167-180); n_inner_host[B] receives
- * the number of sweeps executed. */
+ * the number of sweeps executed and err_host[B] the `err` of the last sweep (update_dual_oneiter's third
+ * return value, update_fns_in_pdhg.py:162-165); either may be NULL.  Sweeps use cfg.rho_alp_iters. */
 int pdhg_update_dual(pdhg_handle* h, const double* phi_bar_dev, const double* rho_prev_dev,
                      const double* alp_prev_dev, const double* epsl_host, double sigma, double eps,
-                     double* rho_next_dev, double* alp_next_dev, int32_t* n_inner_host, void* stream);
+                     double* rho_next_dev, double* alp_next_dev, int32_t* n_inner_host, double* err_host,
+                     void* stream);
 
 /* PDHG_solver_oneiter (utils_pdhg_solver.py:9-94) for B instances: iterations [iter_begin, ...) of ONE time
  * block from (phi0, rho0, alp0) with step size stepsz_host[b], until convergence / NaN / n_maxiter /

@@ -21,7 +21,7 @@ cudaError_t launch_init_state(const MarchParams& p, const double* g, int B, cuda
 cudaError_t launch_update_primal(const MarchParams& p, int B, const double* phi_prev, double tau, double* phi_next,
                                  void* ws, cudaStream_t stream, long long* launches);
 cudaError_t launch_update_dual(const MarchParams& p, int B, const double* phi_bar, double sigma, double eps,
-                               int* n_inner_dev, void* ws, cudaStream_t stream, long long* launches);
+                               int* n_inner_dev, double* err_dev, void* ws, cudaStream_t stream, long long* launches);
 }  // namespace pdhg
 
 using namespace pdhg;
@@ -58,6 +58,7 @@ struct pdhg_handle {
   int *end_reason = nullptr, *status = nullptr, *blocks_done = nullptr;
   long long* inner_total = nullptr;
   int* n_inner = nullptr;
+  double* err_inner = nullptr;
   void* ws = nullptr;         // cooperative-kernel workspace
   // lazily allocated device mirrors for the *_host entry points
   double *g_dev = nullptr, *phi_all = nullptr, *rho_all = nullptr, *alp_all_ref = nullptr, *alp_all_planar = nullptr;
@@ -200,8 +201,10 @@ extern "C" int pdhg_create(const pdhg_config* cfg, const double* coef_x, const d
   CB(dalloc(h, &h->errlog, B * NB * c.max_rec * kLogCols)); CB(dalloc(h, &h->end_reason, B * NB));
   CB(dalloc(h, &h->status, B)); CB(dalloc(h, &h->blocks_done, B)); CB(dalloc(h, &h->inner_total, B));
   CB(dalloc(h, &h->n_inner, B));
+  CB(dalloc(h, &h->err_inner, B));
   if (c.ndim == 2 && c.n_ctrl > 1) CB(dalloc(h, &h->alp_tmp, B * h->A * c.K * h->n * c.n_ctrl));
-  if (h->path == 2) {
+  {
+    // the cooperative kernel also serves the operator-level entry points, so its workspace always exists
     MarchParams p{};
     p.ndim = c.ndim; p.nx = c.nx; p.ny = c.ny; p.K = c.K;
     const size_t wsb = pdhg_coop_workspace_bytes(p, h->B);
@@ -418,7 +421,7 @@ extern "C" int pdhg_update_primal(pdhg_handle* h, const double* phi_prev, const 
 
 extern "C" int pdhg_update_dual(pdhg_handle* h, const double* phi_bar, const double* rho_prev, const double* alp_prev,
                                 const double* epsl_host, double sigma, double eps, double* rho_next, double* alp_next,
-                                int32_t* n_inner_host, void* stream) {
+                                int32_t* n_inner_host, double* err_host, void* stream) {
   if (!h || !phi_bar || !rho_prev || !alp_prev || !rho_next || !alp_next) return fail(PDHG_ERR_ARG, "pdhg_update_dual: null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CU(cudaSetDevice(h->cfg.device));
@@ -431,11 +434,12 @@ extern "C" int pdhg_update_dual(pdhg_handle* h, const double* phi_bar, const dou
   if (rc) return rc;
   MarchParams p;
   fill_params(h, &p);
-  CU(launch_update_dual(p, h->B, phi_bar, sigma, eps, h->n_inner, h->ws, s, &h->launches));
+  CU(launch_update_dual(p, h->B, phi_bar, sigma, eps, h->n_inner, h->err_inner, h->ws, s, &h->launches));
   CU(cudaMemcpyAsync(rho_next, h->st_rho, B * kn * sizeof(double), cudaMemcpyDeviceToDevice, s));
   rc = alp_from_planar(h, h->st_alp, alp_next, kn, s);
   if (rc) return rc;
   CU(cudaStreamSynchronize(s));
   if (n_inner_host) CU(cudaMemcpy(n_inner_host, h->n_inner, B * sizeof(int), cudaMemcpyDeviceToHost));
+  if (err_host) CU(cudaMemcpy(err_host, h->err_inner, B * sizeof(double), cudaMemcpyDeviceToHost));
   return PDHG_OK;
 }

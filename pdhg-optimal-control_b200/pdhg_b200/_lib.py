@@ -67,7 +67,7 @@ def load():
   lib.pdhg_update_primal.restype = C.c_int
   lib.pdhg_update_primal.argtypes = [vp, dp, dp, dp, dp, dbl, dp, vp]
   lib.pdhg_update_dual.restype = C.c_int
-  lib.pdhg_update_dual.argtypes = [vp, dp, dp, dp, dp, dbl, dbl, dp, dp, dp, vp]
+  lib.pdhg_update_dual.argtypes = [vp, dp, dp, dp, dp, dbl, dbl, dp, dp, dp, dp, vp]
   lib.pdhg_solve_block.restype = C.c_int
   lib.pdhg_solve_block.argtypes = [vp, dp, dp, dp, dp, dp, i64, i64, i64, i32, dp, dp, dp, C.POINTER(Logs), vp]
   lib.pdhg_multi_step.restype = C.c_int
@@ -194,6 +194,7 @@ class Solver:
                       stream=None):
     epsl = _f64(epsl, (self.B,))
     n_inner = np.zeros((self.B,), np.int32)
+    err = np.zeros((self.B,), np.float64)
     _check(self.lib.pdhg_update_dual(self._h, phi_bar_ptr, rho_prev_ptr, alp_prev_ptr, _hptr(epsl), float(sigma),
-                                     float(eps), rho_next_ptr, alp_next_ptr, _hptr(n_inner), stream))
-    return n_inner
+                                     float(eps), rho_next_ptr, alp_next_ptr, _hptr(n_inner), _hptr(err), stream))
+    return n_inner, err
