@@ -97,6 +97,12 @@ void pdhg_destroy(pdhg_handle* h);
 const char* pdhg_last_error(void);
 /* 1 = single-CTA kernel, 2 = cooperative kernel (what `path = 0` resolved to) */
 int pdhg_path(const pdhg_handle* h);
+/* device time (ms, CUDA events on the launch stream) of the solver kernel(s) of the last pdhg_solve_block /
+ * pdhg_multi_step call, excluding the staging copies around them; -1 if none.  Call after the stream is idle. */
+double pdhg_last_kernel_ms(const pdhg_handle* h);
+/* diagnostic: device nanoseconds the last cooperative-kernel march spent in each phase, out6 = {A residual+FFT_y,
+ * B FFT_x+t-solve, C IFFT_y+phi update, D dual sweeps+reduction, -, setup/records/output}; zeros on the single-CTA path */
+int pdhg_phase_times(pdhg_handle* h, double* out6);
 /* number of kernel launches issued through this handle so far */
 int64_t pdhg_launch_count(const pdhg_handle* h);
 

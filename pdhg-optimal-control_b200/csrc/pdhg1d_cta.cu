@@ -53,6 +53,8 @@ __global__ void pdhg1d_cta_kernel(const MarchParams p) {
       for (int i = tid; i < N; i += nth) { rho[i] = grho[i]; a1[i] = galp[i]; a2[i] = galp[N + i]; }
       __syncthreads();
       const double tau = stepsz / 1.5, sigma = stepsz * 1.5;   // utils_pdhg_solver.py:44-46
+      const Recip rc(dt, dx, 1.0, sigma);
+      const double c_dt = p.c_on_rho * rc.idt;
 
       double S_row0, S_rho, S_a1, S_a2;
       {
@@ -82,9 +84,9 @@ __global__ void pdhg1d_cta_kernel(const MarchParams p) {
           const double m2_0 = (r0 + kRhoOffset) * f_minus(-(p.coef_x[x] * a2[i]));
           const double m2_p = (rp + kRhoOffset) * f_minus(-(p.coef_x[xp] * a2[k * nx + xp]));
           const double rnext = (k + 1 < K) ? rho[i + nx] : 0.0;
-          double res = (rnext - r0) / dt + epsl * ((rp + rm - 2 * r0) / (dx * dx));
-          res -= (m1_0 - m1_m) / dx + (m2_p - m2_0) / dx;
-          if (k == K - 1) res += p.c_on_rho / dt;
+          double res = (rnext - r0) * rc.idt + epsl * ((rp + rm - 2 * r0) * rc.idx2);
+          res -= (m1_0 - m1_m) * rc.idx + (m2_p - m2_0) * rc.idx;
+          if (k == K - 1) res += c_dt;
           z0[i] = make_double2(res, 0.0);
         }
         __syncthreads();
@@ -160,14 +162,15 @@ __global__ void pdhg1d_cta_kernel(const MarchParams p) {
             const int xm = (x == 0) ? nx - 1 : x - 1, xp = (x == nx - 1) ? 0 : x + 1;
             const double* pb1 = phib + (k + 1) * nx;
             const double c0 = pb1[x], cm = pb1[xm], cp = pb1[xp];
-            const double dxr = (cp - c0) / dx, dxl = (c0 - cm) / dx;
+            const double dxr = (cp - c0) * rc.idx, dxl = (c0 - cm) * rc.idx;
             const double ro = rho[i], a1o = a1[i], a2o = a2[i];
             const double cf = p.coef_x[x];
-            const double pinv = (ro + kRhoOffset) / sigma;
-            const double a1n = prox_alp(egno, a1o, dxr, pinv, cf, true);
-            const double a2n = prox_alp(egno, a2o, dxl, pinv, cf, false);
+            const double pinv = (ro + kRhoOffset) * rc.isig;
+            const double rinv = prox_rinv(egno, pinv);
+            const double a1n = prox_alp(egno, a1o, dxr, pinv, rinv, cf, true);
+            const double a2n = prox_alp(egno, a2o, dxl, pinv, rinv, cf, false);
             const double f1 = f_plus(-(cf * a1n)), f2 = f_minus(-(cf * a2n));
-            double vec = (c0 - phib[k * nx + x]) / dt - epsl * ((cp + cm - 2 * c0) / (dx * dx));
+            double vec = (c0 - phib[k * nx + x]) * rc.idt - epsl * ((cp + cm - 2 * c0) * rc.idx2);
             vec -= dxr * f1 + dxl * f2;
             vec -= lagr(egno, a1n) + lagr(egno, a2n);
             const double rn = relu_nan(ro + sigma * vec);

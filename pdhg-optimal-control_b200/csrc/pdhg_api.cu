@@ -15,6 +15,7 @@ cudaError_t launch_pdhg1d_cta(const MarchParams& p, int B, cudaStream_t stream);
 size_t pdhg1d_cta_smem_bytes(int nx, int K);
 cudaError_t launch_pdhg_coop(const MarchParams& p, int B, void* ws, cudaStream_t stream, long long* launches);
 size_t pdhg_coop_workspace_bytes(const MarchParams& p, int B);
+cudaError_t coop_phase_times(const MarchParams& p, void* ws, double* out6);
 cudaError_t launch_pack_alp(const double* ref_layout, double* planar, int B, int A, size_t kn, int n_ctrl, int ndim,
                             int egno, int to_planar, cudaStream_t stream);
 cudaError_t launch_init_state(const MarchParams& p, const double* g, int B, cudaStream_t stream);
@@ -60,6 +61,8 @@ struct pdhg_handle {
   int* n_inner = nullptr;
   double* err_inner = nullptr;
   void* ws = nullptr;         // cooperative-kernel workspace
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the solver kernel(s) of the last march on its stream
+  bool ev_valid = false;
   // lazily allocated device mirrors for the *_host entry points
   double *g_dev = nullptr, *phi_all = nullptr, *rho_all = nullptr, *alp_all_ref = nullptr, *alp_all_planar = nullptr;
   // scratch for reference-layout <-> planar conversion of single-block alp
@@ -113,12 +116,32 @@ extern "C" const char* pdhg_last_error(void) { return g_err.c_str(); }
 extern "C" void pdhg_destroy(pdhg_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
   for (void* p : h->owned) cudaFree(p);
   delete h;
 }
 
 extern "C" int pdhg_path(const pdhg_handle* h) { return h ? h->path : 0; }
+extern "C" double pdhg_last_kernel_ms(const pdhg_handle* h) {
+  if (!h || !h->ev_valid) return -1.0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
 extern "C" int64_t pdhg_launch_count(const pdhg_handle* h) { return h ? h->launches : 0; }
+
+static void fill_params(pdhg_handle* h, MarchParams* p);
+
+extern "C" int pdhg_phase_times(pdhg_handle* h, double* out6) {
+  if (!h || !out6) return fail(PDHG_ERR_ARG, "pdhg_phase_times: null argument");
+  if (h->path != 2) { for (int i = 0; i < 6; ++i) out6[i] = 0.0; return PDHG_OK; }
+  MarchParams p;
+  fill_params(h, &p);
+  CU(cudaSetDevice(h->cfg.device));
+  CU(coop_phase_times(p, h->ws, out6));
+  return PDHG_OK;
+}
 
 extern "C" int pdhg_create(const pdhg_config* cfg, const double* coef_x, const double* coef_y, pdhg_handle** out) {
   if (!cfg || !out || !coef_x) return fail(PDHG_ERR_ARG, "pdhg_create: null argument");
@@ -270,6 +293,9 @@ static int download_logs(pdhg_handle* h, int nblocks, pdhg_logs* logs, cudaStrea
 }
 
 static int run_march(pdhg_handle* h, const MarchParams& p, cudaStream_t s) {
+  if (!h->ev0) { CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1)); }
+  CU(cudaEventRecord(h->ev0, s));
+  struct Rec { pdhg_handle* h; cudaStream_t s; ~Rec() { h->ev_valid = (cudaEventRecord(h->ev1, s) == cudaSuccess); } } rec{h, s};
   if (h->path == 1) {
     CU(launch_pdhg1d_cta(p, h->B, s));
     h->launches += 1;

@@ -23,7 +23,8 @@ namespace cg = cooperative_groups;
 namespace pdhg {
 
 constexpr int kNQ = 20;        // reduced quantities per epoch
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
 
 struct CoopWs {
   double* phi[2];     // ping-pong phi [(K+1) n]
@@ -32,8 +33,9 @@ struct CoopWs {
   double* alp[2];     // ping-pong alp [A][K n]
   double2* zt;        // [K][nyh][nx] half spectrum, transposed
   double* partials;   // [2][grid][kNQ]
-  double* den;        // [K][nyh][nx]  Thomas pivots        (K > 1)
+  double* den;        // [K][nyh][nx]  reciprocal Thomas pivots (K > 1)
   double* tu;         // [K][nyh][nx]  modified super-diag  (K > 1)
+  double* phase_ns;   // [8] accumulated device time per phase of the last march (A, B, C, D+reduce, records, setup/output)
 };
 
 enum : int { MODE_MARCH = 0, MODE_PRIMAL = 1, MODE_DUAL = 2, MODE_TABLES = 3 };
@@ -66,10 +68,24 @@ struct CoopArgs {
 struct Ctx {
   const CoopArgs& a;
   cg::grid_group grid;
-  double2* sm;        // dynamic shared memory
-  double* red;        // [kNQ*8] static scratch
+  const double2* twx;   // smem copies of the twiddle / coefficient tables (L1 is flushed by every grid sync)
+  const double2* twy;
+  const double* cx;
+  const double* cy;
+  double2* work;        // FFT buffers
+  double* red;          // [kNQ*kWarps] static scratch
   int epoch;
-  __device__ Ctx(const CoopArgs& a_, double2* sm_, double* red_) : a(a_), grid(cg::this_grid()), sm(sm_), red(red_), epoch(0) {}
+  __device__ Ctx(const CoopArgs& a_, double2* sm, double* red_) : a(a_), grid(cg::this_grid()), red(red_), epoch(0) {
+    double2* tx = sm;
+    double2* ty = tx + a.nxe;
+    double* px = reinterpret_cast<double*>(ty + a.nye);
+    double* py = px + a.nxe;
+    for (int i = threadIdx.x; i < a.nxe; i += blockDim.x) { tx[i] = a.tw_xe[i]; px[i] = a.coef_xe[i]; }
+    for (int i = threadIdx.x; i < a.nye; i += blockDim.x) { ty[i] = a.tw_ye[i]; py[i] = a.coef_ye[i]; }
+    twx = tx; twy = ty; cx = px; cy = py;
+    work = reinterpret_cast<double2*>(py + a.nye + ((a.nxe + a.nye) & 1));
+    __syncthreads();
+  }
 };
 
 // ---- neighbour index helpers (bc 0 periodic; bc 1 Neumann, utils_diff_op.py:19-22,61-64,219-224) ----
@@ -82,117 +98,185 @@ __device__ __forceinline__ Nbr nbr(int i, int n, int bc) {
   return r;
 }
 
-// grid-wide sum of kNQ per-thread values; result broadcast to every thread of every CTA (deterministic order).
-__device__ void grid_sum(Ctx& c, double (&v)[kNQ]) {
+// VW-wide (1 or 2 doubles) global access; VW = 2 needs 16-byte alignment (even index on a 256-B aligned array)
+template <int VW> struct Vec { double e[VW]; };
+template <int VW> __device__ __forceinline__ Vec<VW> ldv(const double* p) {
+  Vec<VW> r;
+  if (VW == 2) { const double2 t = *reinterpret_cast<const double2*>(p); r.e[0] = t.x; r.e[VW - 1] = t.y; }
+  else r.e[0] = *p;
+  return r;
+}
+template <int VW> __device__ __forceinline__ void stv(double* p, const Vec<VW>& v) {
+  if (VW == 2) *reinterpret_cast<double2*>(p) = make_double2(v.e[0], v.e[VW - 1]);
+  else *p = v.e[0];
+}
+
+// Reductions.  Every phase block-reduces its per-thread sums and writes ONE row of CTA partials (slot0..slot0+N-1 of
+// the current epoch's buffer); after the next grid sync `grid_gather` sums the rows of all CTAs in a fixed order, so
+// every thread of every CTA holds bit-identical totals and takes identical decisions.
+template <int N>
+__device__ __forceinline__ void cta_partials(Ctx& c, const double (&vals)[N], int slot0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  const int G = gridDim.x;
+  double t[N];
 #pragma unroll
-  for (int q = 0; q < kNQ; ++q) {
+  for (int q = 0; q < N; ++q) {
+    t[q] = vals[q];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+    for (int o = 16; o > 0; o >>= 1) t[q] += __shfl_xor_sync(0xffffffffu, t[q], o);
   }
   __syncthreads();
   if (lane == 0) {
 #pragma unroll
-    for (int q = 0; q < kNQ; ++q) c.red[q * 8 + warp] = v[q];
+    for (int q = 0; q < N; ++q) c.red[q * kWarps + warp] = t[q];
   }
   __syncthreads();
-  double* part = c.a.w.partials + (size_t)(c.epoch & 1) * G * kNQ;
-  if (tid < kNQ) {
-    double t = 0.0;
-    for (int w = 0; w < nw; ++w) t += c.red[tid * 8 + w];
-    part[(size_t)blockIdx.x * kNQ + tid] = t;
+  if (tid < N) {
+    double acc = 0.0;
+    for (int w = 0; w < nw; ++w) acc += c.red[tid * kWarps + w];
+    double* part = c.a.w.partials + (size_t)(c.epoch & 1) * gridDim.x * kNQ;
+    part[(size_t)blockIdx.x * kNQ + slot0 + tid] = acc;
   }
+}
+
+__device__ __forceinline__ void grid_gather(Ctx& c, double (&v)[kNQ]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int G = gridDim.x;
+  const double* part = c.a.w.partials + (size_t)(c.epoch & 1) * G * kNQ;
   c.grid.sync();
-  // every CTA reduces all partials: warp w handles quantities w, w+nw, ...
   for (int q = warp; q < kNQ; q += nw) {
     double t = 0.0;
-    for (int g = lane; g < G; g += 32) t += *((volatile double*)&part[(size_t)g * kNQ + q]);
+    for (int g = lane; g < G; g += 32) t += *((const volatile double*)&part[(size_t)g * kNQ + q]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) c.red[q * 8] = t;
+    if (lane == 0) c.red[q * kWarps] = t;
   }
   __syncthreads();
 #pragma unroll
-  for (int q = 0; q < kNQ; ++q) v[q] = c.red[q * 8];
+  for (int q = 0; q < kNQ; ++q) v[q] = c.red[q * kWarps];
   __syncthreads();
   c.epoch++;
 }
 
+// continuity residual at one point (update_fns_in_pdhg.py:72-96).  Index 0 = the point, m/p = its -/+ neighbour.
+template <int ND>
+__device__ __forceinline__ double cont_point(int egno, bool last_k, double r00, double rnext, double rym, double ryp, double rxm,
+                                             double rxp, double a1y_0, double a1y_m, double a2y_0, double a2y_p, double a1x_0,
+                                             double a1x_m, double a2x_0, double a2x_p, double cy0, double cym, double cyp, double cx0,
+                                             double cxm, double cxp, double wxm, double wxp, double epsl, const Recip& rc,
+                                             double c_dt) {
+  double f1y_0, f1y_m, f2y_0, f2y_p;
+  if (egno == 3) {
+    f1y_0 = f_plus(cx0); f1y_m = f1y_0; f2y_0 = f_minus(cx0); f2y_p = f2y_0;     // f_y = x (velocity), set_fns.py:98
+  } else {
+    f1y_0 = f_plus(-(cy0 * a1y_0)); f1y_m = f_plus(-(cym * a1y_m));
+    f2y_0 = f_minus(-(cy0 * a2y_0)); f2y_p = f_minus(-(cyp * a2y_p));
+  }
+  const double m1y_0 = (r00 + kRhoOffset) * f1y_0, m1y_m = (rym + kRhoOffset) * f1y_m;
+  const double m2y_0 = (r00 + kRhoOffset) * f2y_0, m2y_p = (ryp + kRhoOffset) * f2y_p;
+  double res;
+  if (ND == 2) {
+    double f1x_0, f1x_m, f2x_0, f2x_p;
+    if (egno == 3) {
+      f1x_0 = f_plus(a1x_0); f1x_m = f_plus(a1x_m); f2x_0 = f_minus(a2x_0); f2x_p = f_minus(a2x_p);
+    } else {
+      f1x_0 = f_plus(-(cx0 * a1x_0)); f1x_m = f_plus(-(cxm * a1x_m));
+      f2x_0 = f_minus(-(cx0 * a2x_0)); f2x_p = f_minus(-(cxp * a2x_p));
+    }
+    const double m1x_0 = (r00 + kRhoOffset) * f1x_0, m1x_m = (rxm + kRhoOffset) * f1x_m;
+    const double m2x_0 = (r00 + kRhoOffset) * f2x_0, m2x_p = (rxp + kRhoOffset) * f2x_p;
+    res = (rnext - r00) * rc.idt + epsl * ((rxp + rxm - 2 * r00) * rc.idx2) + epsl * ((ryp + rym - 2 * r00) * rc.idy2);
+    res -= wxm * (m1x_0 - m1x_m) * rc.idx + wxp * (m2x_p - m2x_0) * rc.idx + (m1y_0 - m1y_m) * rc.idy + (m2y_p - m2y_0) * rc.idy;
+  } else {
+    res = (rnext - r00) * rc.idt + epsl * ((ryp + rym - 2 * r00) * rc.idy2);
+    res -= (m1y_0 - m1y_m) * rc.idy + (m2y_p - m2y_0) * rc.idy;
+  }
+  if (last_k) res += c_dt;
+  return res;
+}
+
 // ---- phase A: residual rows -> y-FFT -> transposed half spectrum ----
-__device__ void phase_A(Ctx& c, int cd, double epsl) {
+template <int ND, int VW>
+__device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
   const CoopArgs& a = c.a;
   const MarchParams& p = a.p;
   const int K = p.K, nx = a.nxe, ny = a.nye, nyh = a.nyh, TR = a.TR;
   const size_t n = (size_t)nx * ny, KN = (size_t)K * n;
   const int rows = K * nx, ntiles = (rows + TR - 1) / TR;
   const int ld = ny + 1;
-  double2* buf0 = c.sm;
+  double2* buf0 = c.work;
   double2* buf1 = buf0 + (size_t)(TR / 2) * ld;
   const double* rho = a.w.rho[cd];
   const double* al = a.w.alp[cd];
+  const double* a1x = al;
+  const double* a2x = al + KN;
+  const double* a1y = al + (size_t)(2 * ND - 2) * KN;
+  const double* a2y = al + (size_t)(2 * ND - 1) * KN;
   const int tid = threadIdx.x, nth = blockDim.x;
   const int egno = p.egno;
-  const double dt = p.dt, dx = a.dxe, dy = a.dye;
+  const Recip rc(p.dt, a.dxe, a.dye, 1.0);
+  const double c_dt = p.c_on_rho * rc.idt;
+  const int ny2 = ny / VW;
+  const int dlr = nth / ny2, djp = nth - dlr * ny2;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int r0 = tile * TR;
     const int nrows = min(TR, rows - r0), npairs = (nrows + 1) >> 1;
-    for (int idx = tid; idx < npairs * 2 * ny; idx += nth) {
-      const int lr = idx / ny, j = idx - lr * ny;
-      double res = 0.0;
+    int lr = tid / ny2, jp = tid - lr * ny2;
+    while (lr < 2 * npairs) {
+      const int j = jp * VW;
+      Vec<VW> res;
+#pragma unroll
+      for (int e = 0; e < VW; ++e) res.e[e] = 0.0;
       if (lr < nrows) {
         const int r = r0 + lr, k = r / nx, i = r - k * nx;
-        const Nbr by = nbr(j, ny, 0);
         const size_t o = (size_t)k * n + (size_t)i * ny;
-        const double r00 = rho[o + j];
-        const double rnext = (k + 1 < K) ? rho[o + n + j] : 0.0;
-        const double rym = rho[o + by.m], ryp = rho[o + by.p];
-        const double cy0 = a.coef_ye[j];
-        // y direction (the only one in 1-D): control arrays A-2, A-1
-        const double* a1y = al + (size_t)(a.A - 2) * KN;
-        const double* a2y = al + (size_t)(a.A - 1) * KN;
-        double f1y_0, f1y_m, f2y_0, f2y_p;
-        if (egno == 3) {
-          const double xi = a.coef_xe[i];
-          f1y_0 = f_plus(xi); f1y_m = f1y_0; f2y_0 = f_minus(xi); f2y_p = f2y_0;
-        } else {
-          f1y_0 = f_plus(-(cy0 * a1y[o + j]));
-          f1y_m = f_plus(-(a.coef_ye[by.m] * a1y[o + by.m]));
-          f2y_0 = f_minus(-(cy0 * a2y[o + j]));
-          f2y_p = f_minus(-(a.coef_ye[by.p] * a2y[o + by.p]));
+        const int jm = (j == 0) ? ny - 1 : j - 1, jq = (j + VW == ny) ? 0 : j + VW;
+        const Vec<VW> r00 = ldv<VW>(rho + o + j);
+        Vec<VW> rnext;
+        if (k + 1 < K) rnext = ldv<VW>(rho + o + n + j);
+        else {
+#pragma unroll
+          for (int e = 0; e < VW; ++e) rnext.e[e] = 0.0;
         }
-        const double m1y_0 = (r00 + kRhoOffset) * f1y_0, m1y_m = (rym + kRhoOffset) * f1y_m;
-        const double m2y_0 = (r00 + kRhoOffset) * f2y_0, m2y_p = (ryp + kRhoOffset) * f2y_p;
-        if (a.has_x) {
-          const Nbr bx = nbr(i, nx, p.bc_x);
+        const double r_l = rho[o + jm], r_r = rho[o + jq];
+        Vec<VW> v1y, v2y;
+        double a1y_l = 0.0, a2y_r = 0.0;
+        if (egno != 3) {
+          v1y = ldv<VW>(a1y + o + j); v2y = ldv<VW>(a2y + o + j);
+          a1y_l = a1y[o + jm]; a2y_r = a2y[o + jq];
+        } else {
+#pragma unroll
+          for (int e = 0; e < VW; ++e) { v1y.e[e] = 0.0; v2y.e[e] = 0.0; }
+        }
+        Vec<VW> rxm, rxp, v1x, v1xm, v2x, v2xp;
+        Nbr bx = nbr(i, nx, p.bc_x);
+        if (ND == 2) {
           const size_t om = (size_t)k * n + (size_t)bx.m * ny, op = (size_t)k * n + (size_t)bx.p * ny;
-          const double rxm = rho[om + j], rxp = rho[op + j];
-          const double* a1x = al;
-          const double* a2x = al + KN;
-          double f1x_0, f1x_m, f2x_0, f2x_p;
-          if (egno == 3) {
-            f1x_0 = f_plus(a1x[o + j]); f1x_m = f_plus(a1x[om + j]);
-            f2x_0 = f_minus(a2x[o + j]); f2x_p = f_minus(a2x[op + j]);
-          } else {
-            f1x_0 = f_plus(-(a.coef_xe[i] * a1x[o + j]));
-            f1x_m = f_plus(-(a.coef_xe[bx.m] * a1x[om + j]));
-            f2x_0 = f_minus(-(a.coef_xe[i] * a2x[o + j]));
-            f2x_p = f_minus(-(a.coef_xe[bx.p] * a2x[op + j]));
-          }
-          const double m1x_0 = (r00 + kRhoOffset) * f1x_0, m1x_m = (rxm + kRhoOffset) * f1x_m;
-          const double m2x_0 = (r00 + kRhoOffset) * f2x_0, m2x_p = (rxp + kRhoOffset) * f2x_p;
-          res = (rnext - r00) / dt + epsl * ((rxp + rxm - 2 * r00) / (dx * dx)) + epsl * ((ryp + rym - 2 * r00) / (dy * dy));
-          res -= bx.wm * (m1x_0 - m1x_m) / dx + bx.wp * (m2x_p - m2x_0) / dx + (m1y_0 - m1y_m) / dy + (m2y_p - m2y_0) / dy;
-        } else {
-          res = (rnext - r00) / dt + epsl * ((ryp + rym - 2 * r00) / (dy * dy));
-          res -= (m1y_0 - m1y_m) / dy + (m2y_p - m2y_0) / dy;
+          rxm = ldv<VW>(rho + om + j); rxp = ldv<VW>(rho + op + j);
+          v1x = ldv<VW>(a1x + o + j); v1xm = ldv<VW>(a1x + om + j);
+          v2x = ldv<VW>(a2x + o + j); v2xp = ldv<VW>(a2x + op + j);
         }
-        if (k == K - 1) res += p.c_on_rho / dt;
+        const double cx0 = (ND == 2 || egno == 3) ? c.cx[i] : 0.0;
+        const double cxm = (ND == 2) ? c.cx[bx.m] : 0.0, cxp = (ND == 2) ? c.cx[bx.p] : 0.0;
+#pragma unroll
+        for (int e = 0; e < VW; ++e) {
+          const double rym = (e == 0) ? r_l : r00.e[0], ryp = (e == VW - 1) ? r_r : r00.e[VW - 1];
+          const double a1m = (e == 0) ? a1y_l : v1y.e[0], a2p = (e == VW - 1) ? a2y_r : v2y.e[VW - 1];
+          const int je = j + e;
+          const double cym = c.cy[(e == 0) ? jm : j], cyp = c.cy[(e == VW - 1) ? jq : j + VW - 1];
+          res.e[e] = cont_point<ND>(egno, k == K - 1, r00.e[e], rnext.e[e], rym, ryp, (ND == 2) ? rxm.e[e] : 0.0, (ND == 2) ? rxp.e[e] : 0.0,
+                                    v1y.e[e], a1m, v2y.e[e], a2p, (ND == 2) ? v1x.e[e] : 0.0, (ND == 2) ? v1xm.e[e] : 0.0,
+                                    (ND == 2) ? v2x.e[e] : 0.0, (ND == 2) ? v2xp.e[e] : 0.0, c.cy[je], cym, cyp, cx0, cxm, cxp, bx.wm, bx.wp,
+                                    epsl, rc, c_dt);
+        }
       }
-      reinterpret_cast<double*>(&buf0[(size_t)(lr >> 1) * ld + j])[lr & 1] = res;
+      double* dst = reinterpret_cast<double*>(&buf0[(size_t)(lr >> 1) * ld + j]) + (lr & 1);
+#pragma unroll
+      for (int e = 0; e < VW; ++e) dst[2 * e] = res.e[e];
+      lr += dlr; jp += djp;
+      if (jp >= ny2) { jp -= ny2; ++lr; }
     }
     __syncthreads();
-    double2* zf = fft_rows(buf0, buf1, a.plan_ye, ld, a.tw_ye, npairs, 1.0);
+    double2* zf = fft_rows(buf0, buf1, a.plan_ye, ld, c.twy, npairs, 1.0);
     for (int idx = tid; idx < npairs * nyh; idx += nth) {
       const int ky = idx / npairs, pr = idx - ky * npairs;
       const int kym = (ky == 0) ? 0 : ny - ky;
@@ -208,137 +292,136 @@ __device__ void phase_A(Ctx& c, int cd, double epsl) {
   }
 }
 
+// Thomas recurrences over k for one real component of one Fourier mode (item w of a [K][2*modes] real array)
+__device__ __forceinline__ void thomas_component(double* ztd, const double* den, const double* tu, int K, size_t modes2, size_t w,
+                                                 double ct2) {
+  const size_t m = w >> 1, modes = modes2 >> 1;
+  double bp = 0.0;
+  int k = 0;
+  for (; k + 4 <= K; k += 4) {      // 4 independent loads ahead of the dependent chain
+    double v[4], dn[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { v[q] = ztd[(size_t)(k + q) * modes2 + w]; dn[q] = den[(size_t)(k + q) * modes + m]; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { bp = (v[q] + ct2 * bp) * dn[q]; ztd[(size_t)(k + q) * modes2 + w] = bp; }
+  }
+  for (; k < K; ++k) {
+    bp = (ztd[(size_t)k * modes2 + w] + ct2 * bp) * den[(size_t)k * modes + m];
+    ztd[(size_t)k * modes2 + w] = bp;
+  }
+  double xs = bp;
+  k = K - 2;
+  for (; k - 3 >= 0; k -= 4) {
+    double v[4], tv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { v[q] = ztd[(size_t)(k - q) * modes2 + w]; tv[q] = tu[(size_t)(k - q) * modes + m]; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { xs = v[q] - tv[q] * xs; ztd[(size_t)(k - q) * modes2 + w] = xs; }
+  }
+  for (; k >= 0; --k) {
+    xs = ztd[(size_t)k * modes2 + w] - tu[(size_t)k * modes + m] * xs;
+    ztd[(size_t)k * modes2 + w] = xs;
+  }
+}
+
 // ---- phase B: x-FFT, t-solve per mode, inverse x-FFT (in place on zt) ----
-__device__ void phase_B(Ctx& c) {
+__device__ __noinline__ void phase_B(Ctx& c) {
   const CoopArgs& a = c.a;
   const MarchParams& p = a.p;
   const int K = p.K, nx = a.nxe, nyh = a.nyh;
   const int tid = threadIdx.x, nth = blockDim.x;
   const double ct2 = p.Ct_over_dt2;
   double2* zt = a.w.zt;
+  const size_t modes = (size_t)nyh * nx;
+  const bool coupled = (K > 1 && ct2 != 0.0);
   if (nx == 1) {
-    // 1-D: no x transform; thread per mode walks the t direction
-    for (int ky = blockIdx.x * nth + tid; ky < nyh; ky += gridDim.x * nth) {
-      if (K == 1 || ct2 == 0.0) {
-        for (int k = 0; k < K; ++k) {
-          const double d = p.diag[ky] + ((K == 1) ? ct2 : 0.0);
-          double2 v = zt[(size_t)k * nyh + ky];
-          zt[(size_t)k * nyh + ky] = make_double2(v.x / d, v.y / d);
-        }
-      } else {
-        double2 bp = make_double2(0.0, 0.0);
-        for (int k = 0; k < K; ++k) {
-          const double den = a.w.den[(size_t)k * nyh + ky];
-          double2 v = zt[(size_t)k * nyh + ky];
-          bp = make_double2((v.x + ct2 * bp.x) / den, (v.y + ct2 * bp.y) / den);
-          zt[(size_t)k * nyh + ky] = bp;
-        }
-        double2 xs = bp;
-        for (int k = K - 2; k >= 0; --k) {
-          const double t = a.w.tu[(size_t)k * nyh + ky];
-          double2 v = zt[(size_t)k * nyh + ky];
-          xs = make_double2(v.x - t * xs.x, v.y - t * xs.y);
-          zt[(size_t)k * nyh + ky] = xs;
-        }
+    // 1-D: no x transform
+    if (coupled) {
+      for (size_t w = (size_t)blockIdx.x * nth + tid; w < 2 * modes; w += (size_t)gridDim.x * nth)
+        thomas_component(reinterpret_cast<double*>(zt), a.w.den, a.w.tu, K, 2 * modes, w, ct2);
+    } else {
+      const size_t total = (size_t)K * modes;
+      for (size_t g = (size_t)blockIdx.x * nth + tid; g < total; g += (size_t)gridDim.x * nth) {
+        const double d = p.diag[g % modes] + ((K == 1) ? ct2 : 0.0);
+        const double2 v = zt[g];
+        zt[g] = make_double2(v.x / d, v.y / d);
       }
     }
     return;
   }
   const int ld = nx + 1;
   const int TKY = a.TKY;
-  double2* buf0 = c.sm;
+  double2* buf0 = c.work;
   double2* buf1 = buf0 + (size_t)TKY * ld;
-  double2* carry = buf1 + (size_t)TKY * ld;
   const int ntile = (nyh + TKY - 1) / TKY;
-  if (K == 1 || ct2 == 0.0) {
-    // independent (k, ky) rows: FFT -> divide -> IFFT
-    for (int u = blockIdx.x; u < K * ntile; u += gridDim.x) {
-      const int k = u / ntile, ky0 = (u - k * ntile) * TKY;
-      const int nr = min(TKY, nyh - ky0);
-      for (int idx = tid; idx < nr * nx; idx += nth) {
-        const int t = idx / nx, kx = idx - t * nx;
-        buf0[(size_t)t * ld + kx] = zt[((size_t)k * nyh + ky0 + t) * nx + kx];
-      }
-      __syncthreads();
-      double2* zf = fft_rows(buf0, buf1, a.plan_xe, ld, a.tw_xe, nr, 1.0);
+  const int nunits = K * ntile;
+  // pass 1: x-FFT of every (k, ky) row; uncoupled modes are solved and transformed back in the same pass
+  for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+    const int k = u / ntile, ky0 = (u - k * ntile) * TKY;
+    const int nr = min(TKY, nyh - ky0);
+    for (int idx = tid; idx < nr * nx; idx += nth) {
+      const int t = idx / nx, kx = idx - t * nx;
+      buf0[(size_t)t * ld + kx] = zt[((size_t)k * nyh + ky0 + t) * nx + kx];
+    }
+    __syncthreads();
+    double2* zf = fft_rows(buf0, buf1, a.plan_xe, ld, c.twx, nr, 1.0);
+    if (!coupled) {
       double2* zo = (zf == buf0) ? buf1 : buf0;
       for (int idx = tid; idx < nr * nx; idx += nth) {
         const int t = idx / nx, kx = idx - t * nx;
-        const double d = p.diag[(size_t)kx * nyh + ky0 + t] + ((K == 1) ? ct2 : 0.0);
-        double2 v = zf[(size_t)t * ld + kx];
-        zf[(size_t)t * ld + kx] = make_double2(v.x / d, v.y / d);
-      }
-      __syncthreads();
-      double2* zu = fft_rows(zf, zo, a.plan_xe, ld, a.tw_xe, nr, -1.0);
-      for (int idx = tid; idx < nr * nx; idx += nth) {
-        const int t = idx / nx, kx = idx - t * nx;
-        zt[((size_t)k * nyh + ky0 + t) * nx + kx] = zu[(size_t)t * ld + kx];
-      }
-      __syncthreads();
-    }
-    return;
-  }
-  // K > 1: forward elimination over k (carry = b_{k-1}), then back-substitution + inverse FFT
-  for (int u = blockIdx.x; u < ntile; u += gridDim.x) {
-    const int ky0 = u * TKY;
-    const int nr = min(TKY, nyh - ky0);
-    for (int k = 0; k < K; ++k) {
-      for (int idx = tid; idx < nr * nx; idx += nth) {
-        const int t = idx / nx, kx = idx - t * nx;
-        buf0[(size_t)t * ld + kx] = zt[((size_t)k * nyh + ky0 + t) * nx + kx];
-      }
-      __syncthreads();
-      double2* zf = fft_rows(buf0, buf1, a.plan_xe, ld, a.tw_xe, nr, 1.0);
-      for (int idx = tid; idx < nr * nx; idx += nth) {
-        const int t = idx / nx, kx = idx - t * nx;
-        const size_t g = ((size_t)k * nyh + ky0 + t) * nx + kx;
-        const double den = a.w.den[g];
+        const double rd = 1.0 / (p.diag[(size_t)kx * nyh + ky0 + t] + ((K == 1) ? ct2 : 0.0));
         const double2 v = zf[(size_t)t * ld + kx];
-        const double2 bp = (k == 0) ? make_double2(0.0, 0.0) : carry[(size_t)t * nx + kx];
-        const double2 bn = make_double2((v.x + ct2 * bp.x) / den, (v.y + ct2 * bp.y) / den);
-        carry[(size_t)t * nx + kx] = bn;
-        zt[g] = bn;
+        zf[(size_t)t * ld + kx] = make_double2(v.x * rd, v.y * rd);
       }
       __syncthreads();
+      zf = fft_rows(zf, zo, a.plan_xe, ld, c.twx, nr, -1.0);
     }
-    for (int k = K - 1; k >= 0; --k) {
-      for (int idx = tid; idx < nr * nx; idx += nth) {
-        const int t = idx / nx, kx = idx - t * nx;
-        const size_t g = ((size_t)k * nyh + ky0 + t) * nx + kx;
-        double2 xs;
-        if (k == K - 1) {
-          xs = carry[(size_t)t * nx + kx];
-        } else {
-          const double tuv = a.w.tu[g];
-          const double2 v = zt[g], xn = carry[(size_t)t * nx + kx];
-          xs = make_double2(v.x - tuv * xn.x, v.y - tuv * xn.y);
-          carry[(size_t)t * nx + kx] = xs;
-        }
-        buf0[(size_t)t * ld + kx] = xs;
-      }
-      __syncthreads();
-      double2* zu = fft_rows(buf0, buf1, a.plan_xe, ld, a.tw_xe, nr, -1.0);
-      for (int idx = tid; idx < nr * nx; idx += nth) {
-        const int t = idx / nx, kx = idx - t * nx;
-        zt[((size_t)k * nyh + ky0 + t) * nx + kx] = zu[(size_t)t * ld + kx];
-      }
-      __syncthreads();
+    for (int idx = tid; idx < nr * nx; idx += nth) {
+      const int t = idx / nx, kx = idx - t * nx;
+      zt[((size_t)k * nyh + ky0 + t) * nx + kx] = zf[(size_t)t * ld + kx];
     }
+    __syncthreads();
+  }
+  if (!coupled) return;
+  c.grid.sync();
+  // pass 2: Thomas over k, one thread per real component of a mode (coalesced across modes)
+  for (size_t w = (size_t)blockIdx.x * nth + tid; w < 2 * modes; w += (size_t)gridDim.x * nth)
+    thomas_component(reinterpret_cast<double*>(zt), a.w.den, a.w.tu, K, 2 * modes, w, ct2);
+  c.grid.sync();
+  // pass 3: inverse x-FFT of every row
+  for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+    const int k = u / ntile, ky0 = (u - k * ntile) * TKY;
+    const int nr = min(TKY, nyh - ky0);
+    for (int idx = tid; idx < nr * nx; idx += nth) {
+      const int t = idx / nx, kx = idx - t * nx;
+      buf0[(size_t)t * ld + kx] = zt[((size_t)k * nyh + ky0 + t) * nx + kx];
+    }
+    __syncthreads();
+    double2* zu = fft_rows(buf0, buf1, a.plan_xe, ld, c.twx, nr, -1.0);
+    for (int idx = tid; idx < nr * nx; idx += nth) {
+      const int t = idx / nx, kx = idx - t * nx;
+      zt[((size_t)k * nyh + ky0 + t) * nx + kx] = zu[(size_t)t * ld + kx];
+    }
+    __syncthreads();
   }
 }
 
-// ---- phase C: inverse y-FFT, phi update.  Adds to v[15] (sum dphi^2), v[16] (sum phi_prev^2 rows>=1), v[17] (NaN count)
-__device__ void phase_C(Ctx& c, const double* phi_prev, double* phi_next, double* phib, double tau, double (&v)[kNQ]) {
+// ---- phase C: inverse y-FFT, phi update.  CTA partials: slot 15 (sum dphi^2), 16 (sum phi_prev^2 rows>=1), 17 (NaN count)
+template <int VW>
+__device__ __noinline__ void phase_C(Ctx& c, const double* phi_prev, double* phi_next, double* phib, double tau) {
   const CoopArgs& a = c.a;
   const MarchParams& p = a.p;
   const int K = p.K, nx = a.nxe, ny = a.nye, nyh = a.nyh, TR = a.TR;
   const size_t n = (size_t)nx * ny;
   const int rows = K * nx, ntiles = (rows + TR - 1) / TR;
   const int ld = ny + 1;
-  double2* buf0 = c.sm;
+  double2* buf0 = c.work;
   double2* buf1 = buf0 + (size_t)(TR / 2) * ld;
   const int tid = threadIdx.x, nth = blockDim.x;
   const double inv_nn = 1.0 / ((double)nx * (double)ny);
+  const int ny2 = ny / VW;
+  const int dlr = nth / ny2, djp = nth - dlr * ny2;
+  double s_d = 0.0, s_p = 0.0, s_n = 0.0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int r0 = tile * TR;
     const int nrows = min(TR, rows - r0), npairs = (nrows + 1) >> 1;
@@ -356,100 +439,180 @@ __device__ void phase_C(Ctx& c, const double* phi_prev, double* phi_next, double
       if (ky != 0 && kym != ky) buf0[(size_t)pr * ld + kym] = make_double2(ua.x + ub.y, ub.x - ua.y);
     }
     __syncthreads();
-    double2* zu = fft_rows(buf0, buf1, a.plan_ye, ld, a.tw_ye, npairs, -1.0);
-    for (int idx = tid; idx < nrows * ny; idx += nth) {
-      const int lr = idx / ny, j = idx - lr * ny;
+    double2* zu = fft_rows(buf0, buf1, a.plan_ye, ld, c.twy, npairs, -1.0);
+    int lr = tid / ny2, jp = tid - lr * ny2;
+    while (lr < nrows) {
+      const int j = jp * VW;
       const int r = r0 + lr, k = r / nx, i = r - k * nx;
-      const double2 z = zu[(size_t)(lr >> 1) * ld + j];
-      const double u = ((lr & 1) ? z.y : z.x) * inv_nn;
       const size_t g = (size_t)(k + 1) * n + (size_t)i * ny + j;
-      const double pp = phi_prev[g];
-      const double pn = pp + tau * u;
-      const double df = pn - pp;
-      v[15] += df * df;
-      v[16] += pp * pp;
-      v[17] += is_nan(pn) ? 1.0 : 0.0;
-      phi_next[g] = pn;
-      if (phib) phib[g] = 2 * pn - pp;
+      const double* zsrc = reinterpret_cast<const double*>(&zu[(size_t)(lr >> 1) * ld + j]) + (lr & 1);
+      const Vec<VW> pp = ldv<VW>(phi_prev + g);
+      Vec<VW> pn, pb;
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        const double u = zsrc[2 * e] * inv_nn;
+        pn.e[e] = pp.e[e] + tau * u;
+        const double df = pn.e[e] - pp.e[e];
+        s_d += df * df; s_p += pp.e[e] * pp.e[e]; s_n += is_nan(pn.e[e]) ? 1.0 : 0.0;
+        pb.e[e] = 2 * pn.e[e] - pp.e[e];
+      }
+      stv<VW>(phi_next + g, pn);
+      if (phib) stv<VW>(phib + g, pb);
+      lr += dlr; jp += djp;
+      if (jp >= ny2) { jp -= ny2; ++lr; }
     }
     __syncthreads();
   }
+  const double sums[3] = {s_d, s_p, s_n};
+  cta_partials<3>(c, sums, 15);
 }
 
-// ---- phase D: one dual sweep.  src -> dst (may alias); outer differences against `ref` when ref != nullptr.
-// v[0..1] rho (diff^2, next^2), v[2+2j..3+2j] alp j; v[10] outer rho diff^2, v[11+j] outer alp diff^2; v[18] NaN count of rho_next
-__device__ void phase_D(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d, double* alp_d,
-                        const double* rho_ref, const double* alp_ref, double sigma, double epsl, double (&v)[kNQ]) {
+// dual update at one point (update_fns_in_pdhg.py:99-133,150-165; set_fns.py prox formulas)
+template <int ND>
+__device__ __forceinline__ void dual_point(int egno, double c0, double cxm, double cxp, double cym, double cyp, double pbk, double ro,
+                                           const double (&ao)[2 * ND], double cx, double cy, double wxm, double wxp, double sigma,
+                                           double epsl, const Recip& rc, double& rn, double (&an)[2 * ND]) {
+  const double pinv = (ro + kRhoOffset) * rc.isig;
+  const double rinv = prox_rinv(egno, pinv);
+  const double dyr = (cyp - c0) * rc.idy, dyl = (c0 - cym) * rc.idy;
+  double vec = (c0 - pbk) * rc.idt;
+  double adv = 0.0, L = 0.0;
+  if (ND == 2) {
+    const double dxr = wxp * (cxp - c0) * rc.idx, dxl = wxm * (c0 - cxm) * rc.idx;
+    an[0] = prox_alp(egno, ao[0], dxr, pinv, rinv, cx, true);
+    an[1] = prox_alp(egno, ao[1], dxl, pinv, rinv, cx, false);
+    const double f1 = (egno == 3) ? f_plus(an[0]) : f_plus(-(cx * an[0]));
+    const double f2 = (egno == 3) ? f_minus(an[1]) : f_minus(-(cx * an[1]));
+    vec -= epsl * ((cxp + cxm - 2 * c0) * rc.idx2);
+    adv = dxr * f1 + dxl * f2;
+    L = lagr(egno, an[0]) + lagr(egno, an[1]);
+  }
+  constexpr int jy = 2 * ND - 2;
+  double f1, f2;
+  if (egno == 3) {
+    an[jy] = ao[jy]; an[jy + 1] = ao[jy + 1];          // set_fns.py:110: the y pair is passed through
+    f1 = f_plus(cx); f2 = f_minus(cx);
+  } else {
+    an[jy] = prox_alp(egno, ao[jy], dyr, pinv, rinv, cy, true);
+    an[jy + 1] = prox_alp(egno, ao[jy + 1], dyl, pinv, rinv, cy, false);
+    f1 = f_plus(-(cy * an[jy])); f2 = f_minus(-(cy * an[jy + 1]));
+    L += lagr(egno, an[jy]) + lagr(egno, an[jy + 1]);
+  }
+  vec -= epsl * ((cyp + cym - 2 * c0) * rc.idy2);
+  adv += dyr * f1 + dyl * f2;
+  vec -= adv;
+  vec -= L;
+  rn = relu_nan(ro + sigma * vec);
+}
+
+// ---- phase D: one dual sweep.  src -> dst (may alias); outer differences against `ref` when HASREF.
+// CTA partials: slots 0..1 rho (diff^2, next^2), 2+2q..3+2q alp q; 10 outer rho diff^2, 11+q outer alp diff^2; 18 NaN count of rho_next
+template <int ND, int VW, bool HASREF>
+__device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d, double* alp_d,
+                        const double* rho_ref, const double* alp_ref, double sigma, double epsl) {
+  constexpr int NA = 2 * ND;
   const CoopArgs& a = c.a;
   const MarchParams& p = a.p;
-  const int K = p.K, nx = a.nxe, ny = a.nye, egno = p.egno, A = a.A;
+  const int K = p.K, nx = a.nxe, ny = a.nye, egno = p.egno;
   const size_t n = (size_t)nx * ny, KN = (size_t)K * n;
-  const double dt = p.dt, dx = a.dxe, dy = a.dye;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < KN; g += stride) {
-    const int k = (int)(g / n);
-    const size_t rem = g - (size_t)k * n;
-    const int i = (int)(rem / ny), j = (int)(rem - (size_t)i * ny);
-    const double* pb1 = phib + (size_t)(k + 1) * n;
-    const Nbr by = nbr(j, ny, 0);
-    const size_t row = (size_t)i * ny;
-    const double c0 = pb1[row + j], cym = pb1[row + by.m], cyp = pb1[row + by.p];
-    const double dyr = (cyp - c0) / dy, dyl = (c0 - cym) / dy;
-    const double ro = rho_s[g];
-    const double pinv = (ro + kRhoOffset) / sigma;
-    double vec = (c0 - phib[(size_t)k * n + row + j]) / dt;
-    double adv = 0.0, L = 0.0;
-    double an[4], ao[4];
-    if (a.has_x) {
-      const Nbr bx = nbr(i, nx, p.bc_x);
-      const double cxm = pb1[(size_t)bx.m * ny + j], cxp = pb1[(size_t)bx.p * ny + j];
-      const double dxr = bx.wp * (cxp - c0) / dx, dxl = bx.wm * (c0 - cxm) / dx;
-      const double cx = a.coef_xe[i];
-      ao[0] = alp_s[g]; ao[1] = alp_s[KN + g];
-      an[0] = prox_alp(egno, ao[0], dxr, pinv, cx, true);
-      an[1] = prox_alp(egno, ao[1], dxl, pinv, cx, false);
-      const double f1 = (egno == 3) ? f_plus(an[0]) : f_plus(-(cx * an[0]));
-      const double f2 = (egno == 3) ? f_minus(an[1]) : f_minus(-(cx * an[1]));
-      vec -= epsl * ((cxp + cxm - 2 * c0) / (dx * dx));
-      adv = dxr * f1 + dxl * f2;
-      L = lagr(egno, an[0]) + lagr(egno, an[1]);
-    }
-    {
-      const int jy = A - 2;
-      const double cy = a.coef_ye[j];
-      ao[jy] = alp_s[(size_t)jy * KN + g]; ao[jy + 1] = alp_s[(size_t)(jy + 1) * KN + g];
-      double f1, f2;
-      if (egno == 3) {
-        an[jy] = ao[jy]; an[jy + 1] = ao[jy + 1];          // set_fns.py:110: the y pair is passed through
-        const double xi = a.coef_xe[i];
-        f1 = f_plus(xi); f2 = f_minus(xi);
-      } else {
-        an[jy] = prox_alp(egno, ao[jy], dyr, pinv, cy, true);
-        an[jy + 1] = prox_alp(egno, ao[jy + 1], dyl, pinv, cy, false);
-        f1 = f_plus(-(cy * an[jy])); f2 = f_minus(-(cy * an[jy + 1]));
-        L += lagr(egno, an[jy]) + lagr(egno, an[jy + 1]);
-      }
-      vec -= epsl * ((cyp + cym - 2 * c0) / (dy * dy));
-      adv += dyr * f1 + dyl * f2;
-    }
-    vec -= adv;
-    vec -= L;
-    const double rn = relu_nan(ro + sigma * vec);
-    rho_d[g] = rn;
-    double d = rn - ro;
-    v[0] += d * d; v[1] += rn * rn;
-    v[18] += is_nan(rn) ? 1.0 : 0.0;
-    if (rho_ref) { d = rn - rho_ref[g]; v[10] += d * d; }
+  const Recip rc(p.dt, a.dxe, a.dye, sigma);
+  const int lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int ny2 = ny / VW, nchunk = (ny2 + 31) >> 5;
+  const long long units = (long long)K * nx * nchunk;
+  double s_dr = 0.0, s_rr = 0.0, s_or = 0.0, s_nan = 0.0;
+  double s_da[NA], s_aa[NA], s_oa[NA];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (q < A) {
-        alp_d[(size_t)q * KN + g] = an[q];
-        d = an[q] - ao[q];
-        v[2 + 2 * q] += d * d; v[3 + 2 * q] += an[q] * an[q];
-        if (alp_ref) { d = an[q] - alp_ref[(size_t)q * KN + g]; v[11 + q] += d * d; }
+  for (int q = 0; q < NA; ++q) { s_da[q] = 0.0; s_aa[q] = 0.0; s_oa[q] = 0.0; }
+  for (long long unit = (long long)blockIdx.x * nwarp + (threadIdx.x >> 5); unit < units; unit += (long long)gridDim.x * nwarp) {
+    const int r = (int)(unit / nchunk), ch = (int)(unit - (long long)r * nchunk);
+    const int jp = ch * 32 + lane;
+    if (jp >= ny2) continue;
+    const int k = r / nx, i = r - k * nx, j = jp * VW;
+    const size_t row = (size_t)i * ny, g = (size_t)k * n + row + j;
+    const double* pb1 = phib + (size_t)(k + 1) * n;
+    const int jm = (j == 0) ? ny - 1 : j - 1, jq = (j + VW == ny) ? 0 : j + VW;
+    const Vec<VW> cc = ldv<VW>(pb1 + row + j);
+    const Vec<VW> pk = ldv<VW>(phib + g);
+    const Vec<VW> ro = ldv<VW>(rho_s + g);
+    Vec<VW> ao[NA];
+#pragma unroll
+    for (int q = 0; q < NA; ++q) ao[q] = ldv<VW>(alp_s + (size_t)q * KN + g);
+    Vec<VW> cxm, cxp;
+    const Nbr bx = nbr(i, nx, p.bc_x);
+    if (ND == 2) { cxm = ldv<VW>(pb1 + (size_t)bx.m * ny + j); cxp = ldv<VW>(pb1 + (size_t)bx.p * ny + j); }
+    const double c_l = pb1[row + jm], c_r = pb1[row + jq];
+    Vec<VW> rref, aref[NA];
+    if (HASREF) {
+      rref = ldv<VW>(rho_ref + g);
+#pragma unroll
+      for (int q = 0; q < NA; ++q) aref[q] = ldv<VW>(alp_ref + (size_t)q * KN + g);
+    }
+    const double cx = (ND == 2 || egno == 3) ? c.cx[i] : 0.0;
+    Vec<VW> rn, an[NA];
+#pragma unroll
+    for (int e = 0; e < VW; ++e) {
+      const double cym = (e == 0) ? c_l : cc.e[0], cyp = (e == VW - 1) ? c_r : cc.e[VW - 1];
+      double aoe[NA], ane[NA], rne;
+#pragma unroll
+      for (int q = 0; q < NA; ++q) aoe[q] = ao[q].e[e];
+      dual_point<ND>(egno, cc.e[e], (ND == 2) ? cxm.e[e] : 0.0, (ND == 2) ? cxp.e[e] : 0.0, cym, cyp, pk.e[e], ro.e[e], aoe, cx,
+                     c.cy[j + e], bx.wm, bx.wp, sigma, epsl, rc, rne, ane);
+      rn.e[e] = rne;
+      double d = rne - ro.e[e];
+      s_dr += d * d; s_rr += rne * rne; s_nan += is_nan(rne) ? 1.0 : 0.0;
+      if (HASREF) { d = rne - rref.e[e]; s_or += d * d; }
+#pragma unroll
+      for (int q = 0; q < NA; ++q) {
+        an[q].e[e] = ane[q];
+        d = ane[q] - aoe[q];
+        s_da[q] += d * d; s_aa[q] += ane[q] * ane[q];
+        if (HASREF) { d = ane[q] - aref[q].e[e]; s_oa[q] += d * d; }
       }
     }
+    stv<VW>(rho_d + g, rn);
+#pragma unroll
+    for (int q = 0; q < NA; ++q) stv<VW>(alp_d + (size_t)q * KN + g, an[q]);
   }
+  double sums[15];
+#pragma unroll
+  for (int q = 0; q < 15; ++q) sums[q] = 0.0;
+  sums[0] = s_dr; sums[1] = s_rr; sums[10] = s_or;
+#pragma unroll
+  for (int q = 0; q < NA; ++q) { sums[2 + 2 * q] = s_da[q]; sums[3 + 2 * q] = s_aa[q]; sums[11 + q] = s_oa[q]; }
+  cta_partials<15>(c, sums, 0);
+  const double sn[1] = {s_nan};
+  cta_partials<1>(c, sn, 18);
+}
+
+// runtime -> compile-time dispatch of the templated phases
+__device__ __forceinline__ void run_A(Ctx& c, int cd, double epsl) {
+  const bool v2 = (c.a.nye & 1) == 0;
+  if (c.a.has_x) { if (v2) phase_A<2, 2>(c, cd, epsl); else phase_A<2, 1>(c, cd, epsl); }
+  else { if (v2) phase_A<1, 2>(c, cd, epsl); else phase_A<1, 1>(c, cd, epsl); }
+}
+__device__ __forceinline__ void run_C(Ctx& c, const double* pp, double* pn, double* pb, double tau) {
+  if ((c.a.nye & 1) == 0) phase_C<2>(c, pp, pn, pb, tau); else phase_C<1>(c, pp, pn, pb, tau);
+}
+__device__ __forceinline__ void run_D(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d, double* alp_d,
+                                      const double* rho_ref, const double* alp_ref, double sigma, double epsl) {
+  const bool v2 = (c.a.nye & 1) == 0;
+  if (rho_ref) {
+    if (c.a.has_x) { if (v2) phase_D<2, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
+                     else phase_D<2, 1, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl); }
+    else { if (v2) phase_D<1, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
+           else phase_D<1, 1, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl); }
+  } else {
+    if (c.a.has_x) { if (v2) phase_D<2, 2, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
+                     else phase_D<2, 1, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
+    else { if (v2) phase_D<1, 2, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
+           else phase_D<1, 1, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
+  }
+}
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
 
 __device__ void grid_copy(double* dst, const double* src, size_t count) {
@@ -471,15 +634,25 @@ __device__ void build_tables(const CoopArgs& a) {
       const double dk = dg + ((k == K - 1) ? ct2 : 2.0 * ct2);
       const double den = (k == 0) ? dk : dk + ct2 * tprev;
       tprev = ((k == K - 1) ? 0.0 : -ct2) / den;
-      a.w.den[(size_t)k * modes + m] = den;
+      a.w.den[(size_t)k * modes + m] = 1.0 / den;      // reciprocal pivot
       a.w.tu[(size_t)k * modes + m] = tprev;
     }
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) pdhg_coop_kernel(const CoopArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) pdhg_coop_kernel(const __grid_constant__ CoopArgs a_param) {
   extern __shared__ __align__(16) double2 dynsm[];
-  __shared__ double red[kNQ * 8];
+  __shared__ double red[kNQ * kWarps];
+  // the argument block is referenced from the (non-inlined) phase functions; keep it in shared memory so that it is
+  // neither spilled to a local-memory copy nor lost with every L1 invalidation of a grid sync
+  __shared__ __align__(16) unsigned char a_smem[sizeof(CoopArgs)];
+  {
+    const unsigned int* src = reinterpret_cast<const unsigned int*>(&a_param);
+    unsigned int* dst = reinterpret_cast<unsigned int*>(a_smem);
+    for (int i = threadIdx.x; i < (int)(sizeof(CoopArgs) / 4); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  }
+  const CoopArgs& a = *reinterpret_cast<const CoopArgs*>(a_smem);
   Ctx c(a, dynsm, red);
   const MarchParams& p = a.p;
   const int tid = threadIdx.x, b = a.b;
@@ -500,14 +673,11 @@ __global__ void __launch_bounds__(kThreads, 1) pdhg_coop_kernel(const CoopArgs a
     grid_copy(w.rho[0], grho, KN);
     grid_copy(w.alp[0], galp, (size_t)A * KN);
     c.grid.sync();
-    phase_A(c, 0, epsl);
+    run_A(c, 0, epsl);
     c.grid.sync();
     phase_B(c);
     c.grid.sync();
-    double v[kNQ];
-#pragma unroll
-    for (int q = 0; q < kNQ; ++q) v[q] = 0.0;
-    phase_C(c, a.op_phi_in, a.op_phi_out, nullptr, a.op_step, v);
+    run_C(c, a.op_phi_in, a.op_phi_out, nullptr, a.op_step);
     grid_copy(a.op_phi_out, a.op_phi_in, n);   // row 0 is invariant (u[0] = 0, utils_precond.py:139)
     return;
   }
@@ -521,13 +691,12 @@ __global__ void __launch_bounds__(kThreads, 1) pdhg_coop_kernel(const CoopArgs a
     double err = 0.0;
     for (; j < p.rho_alp_iters; ++j) {
       double v[kNQ];
-#pragma unroll
-      for (int q = 0; q < kNQ; ++q) v[q] = 0.0;
       const int s = j & 1, d = s ^ 1;
-      phase_D(c, a.op_phi_in, w.rho[s], w.alp[s], w.rho[d], w.alp[d], nullptr, nullptr, a.op_step, epsl, v);
-      grid_sum(c, v);
+      run_D(c, a.op_phi_in, w.rho[s], w.alp[s], w.rho[d], w.alp[d], nullptr, nullptr, a.op_step, epsl);
+      grid_gather(c, v);
       err = v[0] / v[1];
-      for (int q = 0; q < A; ++q) err += v[2 + 2 * q] / v[3 + 2 * q];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (q < A) err += v[2 + 2 * q] / v[3 + 2 * q];
       if (err < a.op_eps) { ++j; break; }
     }
     const int fin = j & 1;     // after j sweeps the latest iterate sits in buffer (j & 1)
@@ -543,6 +712,8 @@ __global__ void __launch_bounds__(kThreads, 1) pdhg_coop_kernel(const CoopArgs a
   int blocks_done = p.blk_begin;
   long long inner_total = 0;
   const int nt_all = p.nblocks * K + 1;
+  unsigned long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = gtimer();
+#define TICK(slot) do { if (lead) { const unsigned long long t_ = gtimer(); tacc[slot] += t_ - tlast; tlast = t_; } } while (0)
 
   for (int blk = p.blk_begin; blk < p.blk_end && status == ST_OK; ++blk) {
     const size_t lb = (size_t)b * p.nblocks + blk;
@@ -558,16 +729,17 @@ __global__ void __launch_bounds__(kThreads, 1) pdhg_coop_kernel(const CoopArgs a
       // initial norms
       double S_row0, S_rho, S_alp[4];
       {
-        double v[kNQ];
-#pragma unroll
-        for (int q = 0; q < kNQ; ++q) v[q] = 0.0;
+        double s6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         const size_t stride = (size_t)gridDim.x * blockDim.x, g0 = (size_t)blockIdx.x * blockDim.x + tid;
-        for (size_t g = g0; g < n; g += stride) { const double x = gphi[g]; v[0] += x * x; }
+        for (size_t g = g0; g < n; g += stride) { const double x = gphi[g]; s6[0] += x * x; }
         for (size_t g = g0; g < KN; g += stride) {
-          const double r = grho[g]; v[1] += r * r;
-          for (int q = 0; q < A; ++q) { const double x = galp[(size_t)q * KN + g]; v[2 + q] += x * x; }
+          const double r = grho[g]; s6[1] += r * r;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (q < A) { const double x = galp[(size_t)q * KN + g]; s6[2 + q] += x * x; }
         }
-        grid_sum(c, v);    // (also orders the copies above before phase A)
+        cta_partials<6>(c, s6, 0);
+        double v[kNQ];
+        grid_gather(c, v);    // (its grid sync also orders the copies above before phase A)
         S_row0 = v[0]; S_rho = v[1];
         for (int q = 0; q < 4; ++q) S_alp[q] = v[2 + q];
       }
@@ -578,42 +750,46 @@ __global__ void __launch_bounds__(kThreads, 1) pdhg_coop_kernel(const CoopArgs a
 
       for (; it < p.n_maxiter; ++it) {
         if (it >= p.iter_pause) { reason = END_PAUSED; break; }
-        phase_A(c, cd, epsl);
+        TICK(5);
+        run_A(c, cd, epsl);
         c.grid.sync();
+        TICK(0);
         phase_B(c);
         c.grid.sync();
+        TICK(1);
         double v[kNQ];
-#pragma unroll
-        for (int q = 0; q < kNQ; ++q) v[q] = 0.0;
-        phase_C(c, w.phi[cp], w.phi[cp ^ 1], w.phib, tau, v);
+        run_C(c, w.phi[cp], w.phi[cp ^ 1], w.phib, tau);
         c.grid.sync();
+        TICK(2);
         // dual sweeps: the first goes cd -> cd^1, the rest in place on cd^1 with outer differences against cd
         const int nd = cd ^ 1;
         double e1s0 = 0.0, e1s1 = 0.0, e1nan = 0.0;
         int j = 0;
         for (; j < p.rho_alp_iters; ++j) {
-          if (j > 0) {
-#pragma unroll
-            for (int q = 0; q < kNQ; ++q) v[q] = 0.0;
-          }
-          if (j == 0) phase_D(c, w.phib, w.rho[cd], w.alp[cd], w.rho[nd], w.alp[nd], nullptr, nullptr, sigma, epsl, v);
-          else phase_D(c, w.phib, w.rho[nd], w.alp[nd], w.rho[nd], w.alp[nd], w.rho[cd], w.alp[cd], sigma, epsl, v);
-          grid_sum(c, v);
+          if (j == 0) run_D(c, w.phib, w.rho[cd], w.alp[cd], w.rho[nd], w.alp[nd], nullptr, nullptr, sigma, epsl);
+          else run_D(c, w.phib, w.rho[nd], w.alp[nd], w.rho[nd], w.alp[nd], w.rho[cd], w.alp[cd], sigma, epsl);
+          grid_gather(c, v);
           if (j == 0) { e1s0 = v[15]; e1s1 = v[16]; e1nan = v[17]; }
           double err = v[0] / v[1];
-          for (int q = 0; q < A; ++q) err += v[2 + 2 * q] / v[3 + 2 * q];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (q < A) err += v[2 + 2 * q] / v[3 + 2 * q];
           if (err < p.eps) { ++j; break; }
         }
         inner_total += j;
+        TICK(3);
         const bool multi = (j > 1);
         err1 = sqrt(e1s0) / sqrt(S_row0 + e1s1);
         err2 = sqrt(multi ? v[10] : v[0]) / sqrt(S_rho);
-        for (int q = 0; q < A; ++q) {
-          const double na = sqrt(S_alp[q]), ne = sqrt(multi ? v[11 + q] : v[2 + 2 * q]);
-          if (na < 1e-6 && ne > 1e-6) err2 += ne; else if (na >= 1e-6) err2 += ne / na;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q < A) {
+            const double na = sqrt(S_alp[q]), ne = sqrt(multi ? v[11 + q] : v[2 + 2 * q]);
+            if (na < 1e-6 && ne > 1e-6) err2 += ne; else if (na >= 1e-6) err2 += ne / na;
+          }
         }
         S_rho = v[1];
-        for (int q = 0; q < A; ++q) S_alp[q] = v[3 + 2 * q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) S_alp[q] = v[3 + 2 * q];
         const bool anynan = (e1nan > 0.0) || (v[18] > 0.0);
         cp ^= 1; cd = nd;       // accept phi_next, rho_next, alp_next
         if (err1 < p.eps && err2 < p.eps) { reason = END_CONVERGED; break; }
@@ -625,11 +801,11 @@ __global__ void __launch_bounds__(kThreads, 1) pdhg_coop_kernel(const CoopArgs a
           for (size_t g = (size_t)blockIdx.x * blockDim.x + tid; g < KN; g += stride) { const double r = w.rho[cd][g]; mn = fmin(mn, r); mx = fmax(mx, r); }
           for (int o = 16; o > 0; o >>= 1) { mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
           __syncthreads();
-          if ((tid & 31) == 0) { red[tid >> 5] = mn; red[8 + (tid >> 5)] = mx; }
+          if ((tid & 31) == 0) { red[tid >> 5] = mn; red[kWarps + (tid >> 5)] = mx; }
           __syncthreads();
           double* part = w.partials + (size_t)(c.epoch & 1) * gridDim.x * kNQ;
           if (tid == 0) {
-            for (int q = 1; q < (int)(blockDim.x >> 5); ++q) { mn = fmin(mn, red[q]); mx = fmax(mx, red[8 + q]); }
+            for (int q = 1; q < (int)(blockDim.x >> 5); ++q) { mn = fmin(mn, red[q]); mx = fmax(mx, red[kWarps + q]); }
             part[(size_t)blockIdx.x * kNQ] = mn; part[(size_t)blockIdx.x * kNQ + 1] = mx;
           }
           c.grid.sync();
@@ -688,12 +864,15 @@ __global__ void __launch_bounds__(kThreads, 1) pdhg_coop_kernel(const CoopArgs a
       break;
     }
   }
+  TICK(5);
   if (lead) {
     p.status[b] = status;
     p.blocks_done[b] = blocks_done;
     p.stepsz[b] = stepsz;
     p.inner_total[b] = inner_total;
+    for (int q = 0; q < 6; ++q) w.phase_ns[q] = (double)tacc[q];
   }
+#undef TICK
 }
 
 // ------------------------------------------- host side -------------------------------------------
@@ -708,15 +887,17 @@ static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   g.nyh = g.nye / 2 + 1;
   const int rows = p.K * g.nxe;
   // y-FFT tile: TR rows (even) -> TR/2 complex transforms, two buffers of (TR/2)*(nye+1) complex
+  const size_t tab = (size_t)24 * (g.nxe + g.nye) + 16;            // twiddles + coefficient tables
+  const size_t cap = smem_cap > tab ? smem_cap - tab : 0;
   int TR = 16;
-  while (TR > 2 && ((rows + TR - 1) / TR < 2 * sm_count || (size_t)TR * (g.nye + 1) * 16 > smem_cap)) TR -= 2;
+  while (TR > 2 && ((rows + TR - 1) / TR < 2 * sm_count || (size_t)TR * (g.nye + 1) * 16 > cap)) TR -= 2;
   g.TR = TR;
-  int TKY = 4;
-  while (TKY > 1 && ((g.nyh + TKY - 1) / TKY < 2 * sm_count || (size_t)3 * TKY * (g.nxe + 1) * 16 > smem_cap)) TKY -= 1;
+  int TKY = 8;
+  while (TKY > 1 && ((size_t)p.K * ((g.nyh + TKY - 1) / TKY) < (size_t)2 * sm_count || (size_t)2 * TKY * (g.nxe + 1) * 16 > cap)) TKY -= 1;
   g.TKY = TKY;
   const size_t smA = (size_t)TR * (g.nye + 1) * 16;                 // 2 buffers * TR/2 rows
-  const size_t smB = (g.nxe > 1) ? (size_t)3 * TKY * (g.nxe + 1) * 16 : 0;
-  g.smem = smA > smB ? smA : smB;
+  const size_t smB = (g.nxe > 1) ? (size_t)2 * TKY * (g.nxe + 1) * 16 : 0;
+  g.smem = tab + (smA > smB ? smA : smB);
   g.grid = sm_count;
   return g;
 }
@@ -745,7 +926,8 @@ static CoopWs carve(const MarchParams& p, void* ws) {
   w.alp[0] = (double*)q; w.alp[1] = w.alp[0] + (size_t)A * KN; q += align_up(2 * A * KN * 8, 256);
   w.zt = (double2*)q; q += align_up((size_t)p.K * modes * 16, 256);
   w.partials = (double*)q; q += align_up((size_t)2 * 1024 * kNQ * 8, 256);
-  w.den = (double*)q; w.tu = w.den + (size_t)p.K * modes;
+  w.den = (double*)q; w.tu = w.den + (size_t)p.K * modes; q += align_up(2 * (size_t)p.K * modes * 8, 256);
+  w.phase_ns = (double*)q;
   return w;
 }
 
@@ -784,6 +966,11 @@ static cudaError_t ensure_tables(const MarchParams& p, void* ws, cudaStream_t st
   if (p.K == 1 || p.Ct_over_dt2 == 0.0) return cudaSuccess;
   ++*launches;
   return coop_launch(p, ws, 0, MODE_TABLES, nullptr, nullptr, 0.0, 0.0, nullptr, nullptr, stream);
+}
+
+cudaError_t coop_phase_times(const MarchParams& p, void* ws, double* out6) {
+  const CoopWs w = carve(p, ws);
+  return cudaMemcpy(out6, w.phase_ns, 6 * sizeof(double), cudaMemcpyDeviceToHost);
 }
 
 cudaError_t launch_pdhg_coop(const MarchParams& p, int B, void* ws, cudaStream_t stream, long long* launches) {

@@ -17,7 +17,7 @@ INST_OK, INST_SOL_NAN, INST_PAUSED, INST_LOG_OVERFLOW = 0, 1, 3, 4
 END_CONVERGED, END_NAN, END_MAXITER, END_PAUSED = 0, 1, 2, 3
 LOG_COLS = 4
 
-EXPORTS = ("pdhg_create", "pdhg_destroy", "pdhg_last_error", "pdhg_path", "pdhg_launch_count", "pdhg_update_primal",
+EXPORTS = ("pdhg_create", "pdhg_destroy", "pdhg_last_error", "pdhg_path", "pdhg_launch_count", "pdhg_last_kernel_ms", "pdhg_phase_times", "pdhg_update_primal",
            "pdhg_update_dual", "pdhg_solve_block", "pdhg_multi_step", "pdhg_multi_step_host")
 
 
@@ -62,6 +62,10 @@ def load():
   lib.pdhg_last_error.argtypes = []
   lib.pdhg_path.restype = C.c_int
   lib.pdhg_path.argtypes = [vp]
+  lib.pdhg_last_kernel_ms.restype = dbl
+  lib.pdhg_last_kernel_ms.argtypes = [vp]
+  lib.pdhg_phase_times.restype = C.c_int
+  lib.pdhg_phase_times.argtypes = [vp, dp]
   lib.pdhg_launch_count.restype = i64
   lib.pdhg_launch_count.argtypes = [vp]
   lib.pdhg_update_primal.restype = C.c_int
@@ -147,6 +151,15 @@ class Solver:
   @property
   def path(self):
     return self.lib.pdhg_path(self._h)
+
+  @property
+  def last_kernel_ms(self):
+    return float(self.lib.pdhg_last_kernel_ms(self._h))
+
+  def phase_times_ms(self):
+    out = np.zeros(6)
+    _check(self.lib.pdhg_phase_times(self._h, _hptr(out)))
+    return dict(zip(("A_residual_ffty", "B_fftx_tsolve", "C_iffty_phi", "D_dual_reduce", "unused", "setup_records_output"), (out / 1e6).tolist()))
 
   @property
   def launch_count(self):
