@@ -100,9 +100,10 @@ int pdhg_path(const pdhg_handle* h);
 /* device time (ms, CUDA events on the launch stream) of the solver kernel(s) of the last pdhg_solve_block /
  * pdhg_multi_step call, excluding the staging copies around them; -1 if none.  Call after the stream is idle. */
 double pdhg_last_kernel_ms(const pdhg_handle* h);
-/* diagnostic: device nanoseconds the last cooperative-kernel march spent in each phase, out6 = {A residual+FFT_y,
- * B FFT_x+t-solve, C IFFT_y+phi update, D dual sweeps+reduction, -, setup/records/output}; zeros on the single-CTA path */
-int pdhg_phase_times(pdhg_handle* h, double* out6);
+/* diagnostic: device nanoseconds the last cooperative-kernel march spent in each phase, out16[0..5] = {A residual+FFT_y,
+ * B FFT_x+t-solve, C IFFT_y+phi update, D dual sweeps+reduction, -, setup/records/output}, out16[6..15] = sub-steps seen
+ * by CTA 0 (A: compute, fft, store; B: pass 1, 2, 3; C: load, fft, update; spare); zeros on the single-CTA path */
+int pdhg_phase_times(pdhg_handle* h, double* out16);
 /* number of kernel launches issued through this handle so far */
 int64_t pdhg_launch_count(const pdhg_handle* h);
 

@@ -13,7 +13,7 @@
 
 namespace pdhg {
 
-__global__ void pdhg1d_cta_kernel(const MarchParams p) {
+__global__ void __launch_bounds__(256, 1) pdhg1d_cta_kernel(const MarchParams p) {
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, nth = blockDim.x;
   const int b = blockIdx.x;
@@ -25,11 +25,12 @@ __global__ void pdhg1d_cta_kernel(const MarchParams p) {
   double* rho = phib + NP;               // [K][nx]
   double* a1 = rho + N;
   double* a2 = a1 + N;
-  double2* z0 = reinterpret_cast<double2*>(a2 + N);   // [K][nx] complex
-  double2* z1 = z0 + N;
+  const int ld = fft_ld(nx);                          // padded FFT row stride (fpad addressing)
+  double2* z0 = reinterpret_cast<double2*>(a2 + N);   // [K][ld] complex
+  double2* z1 = z0 + (size_t)K * ld;
   double* bak = reinterpret_cast<double*>(z0);         // outer-iteration copies of rho/alp (aliases the FFT
                                                        // workspace, which is idle during the dual sweeps)
-  double* red = reinterpret_cast<double*>(z1 + N);     // 9*32 doubles of reduction scratch
+  double* red = reinterpret_cast<double*>(z1 + (size_t)K * ld);     // 9*32 doubles of reduction scratch
 
   double* gphi = p.st_phi + (size_t)b * NP;
   double* grho = p.st_rho + (size_t)b * N;
@@ -87,22 +88,25 @@ __global__ void pdhg1d_cta_kernel(const MarchParams p) {
           double res = (rnext - r0) * rc.idt + epsl * ((rp + rm - 2 * r0) * rc.idx2);
           res -= (m1_0 - m1_m) * rc.idx + (m2_p - m2_0) * rc.idx;
           if (k == K - 1) res += c_dt;
-          z0[i] = make_double2(res, 0.0);
+          z0[k * ld + fpad(x)] = make_double2(res, 0.0);
         }
         __syncthreads();
 
         // ---- H1 preconditioner (utils_precond.py:105-140): FFT_x, per-mode t-solve, IFFT_x ----
-        double2* zf = fft_rows(z0, z1, p.plan_x, nx, p.tw_x, K, 1.0);
+        double2* zf = fft_rows(z0, z1, p.plan_x, ld, p.tw_x, K, 1.0);
         double2* zo = (zf == z0) ? z1 : z0;
         if (K == 1) {
           for (int m = tid; m < nx; m += nth) {
             const double d = p.diag[m] + ct2;
-            zf[m] = make_double2(zf[m].x / d, zf[m].y / d);
+            const int e = fpad(m);
+            zf[e] = make_double2(zf[e].x / d, zf[e].y / d);
           }
         } else if (ct2 == 0.0) {
           for (int i = tid; i < N; i += nth) {
-            const double d = p.diag[i % nx];
-            zf[i] = make_double2(zf[i].x / d, zf[i].y / d);
+            const int k = i / nx, m = i - k * nx;
+            const double d = p.diag[m];
+            const int e = k * ld + fpad(m);
+            zf[e] = make_double2(zf[e].x / d, zf[e].y / d);
           }
         } else {
           double* tu = reinterpret_cast<double*>(zo);   // [K][nx] modified super-diagonal
@@ -111,35 +115,37 @@ __global__ void pdhg1d_cta_kernel(const MarchParams p) {
             double d0 = dg + ((K == 1) ? ct2 : 2.0 * ct2);
             double tprev = -ct2 / d0;
             tu[m] = tprev;
-            double2 bp = make_double2(zf[m].x / d0, zf[m].y / d0);
-            zf[m] = bp;
+            const int em = fpad(m);
+            double2 bp = make_double2(zf[em].x / d0, zf[em].y / d0);
+            zf[em] = bp;
             for (int k = 1; k < K; ++k) {
               const double dk = dg + ((k == K - 1) ? ct2 : 2.0 * ct2);
               const double den = dk + ct2 * tprev;                      // d[k] - dl[k]*tu[k-1], dl = -ct2
               tprev = ((k == K - 1) ? 0.0 : -ct2) / den;
               tu[k * nx + m] = tprev;
-              double2 v = zf[k * nx + m];
+              double2 v = zf[k * ld + em];
               bp = make_double2((v.x + ct2 * bp.x) / den, (v.y + ct2 * bp.y) / den);
-              zf[k * nx + m] = bp;
+              zf[k * ld + em] = bp;
             }
             double2 xs = bp;
             for (int k = K - 2; k >= 0; --k) {
               const double t = tu[k * nx + m];
-              double2 v = zf[k * nx + m];
+              double2 v = zf[k * ld + em];
               xs = make_double2(v.x - t * xs.x, v.y - t * xs.y);
-              zf[k * nx + m] = xs;
+              zf[k * ld + em] = xs;
             }
           }
         }
         __syncthreads();
-        double2* zu = fft_rows(zf, zo, p.plan_x, nx, p.tw_x, K, -1.0);
+        double2* zu = fft_rows(zf, zo, p.plan_x, ld, p.tw_x, K, -1.0);
 
         // ---- phi_next = phi_prev + tau*u ; phi_bar = 2 phi_next - phi_prev (utils_pdhg_solver.py:53-55) ----
         int nanflag = 0;
         double sp[2] = {0.0, 0.0};
         for (int i = tid; i < N; i += nth) {
           const double pp = phi[nx + i];
-          const double pn = pp + tau * (zu[i].x * inv_n);
+          const int kk = i / nx;
+          const double pn = pp + tau * (zu[kk * ld + fpad(i - kk * nx)].x * inv_n);
           const double df = pn - pp;
           sp[0] += df * df;
           sp[1] += pp * pp;
@@ -298,15 +304,16 @@ __global__ void pdhg1d_cta_kernel(const MarchParams p) {
 }
 
 size_t pdhg1d_cta_smem_bytes(int nx, int K) {
-  return ((size_t)(9 * K + 2) * nx + 9 * 32) * sizeof(double);
+  // phi, phi_bar [(K+1) nx] ; rho, alp1, alp2 [K nx] ; two complex FFT buffers [K][fft_ld(nx)] ; reduction scratch
+  return ((size_t)(5 * K + 2) * nx + (size_t)4 * K * fft_ld(nx) + 9 * 32) * sizeof(double);
 }
 
 int pdhg1d_cta_threads(int nx, int K) {
   const int N = nx * K;
-  const int rounds = (N + 383) / 384;
+  const int rounds = (N + 255) / 256;
   int nt = ((N + rounds - 1) / rounds + 31) / 32 * 32;
   if (nt < 64) nt = 64;
-  if (nt > 1024) nt = 1024;
+  if (nt > 256) nt = 256;
   return nt;
 }
 

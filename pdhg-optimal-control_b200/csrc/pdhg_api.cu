@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -79,11 +80,14 @@ static cudaError_t dalloc(pdhg_handle* h, T** p, size_t count) {
   return cudaSuccess;
 }
 
-static bool make_plan(int n, FftPlan* plan) {
+static bool make_plan(int n, FftPlan* plan, int max_radix = 16) {
+  if (const char* e = getenv("PDHG_MAX_RADIX")) max_radix = atoi(e);
   plan->n = n;
   plan->nstages = 0;
   int m = n;
   auto push = [&](int r) { if (plan->nstages < kMaxStages) plan->radix[plan->nstages++] = r; else m = -1; };
+  while (max_radix >= 16 && m > 0 && m % 16 == 0) { push(16); m /= 16; }
+  while (max_radix >= 8 && m > 0 && m % 8 == 0) { push(8); m /= 8; }
   while (m > 0 && m % 4 == 0) { push(4); m /= 4; }
   while (m > 0 && m % 2 == 0) { push(2); m /= 2; }
   while (m > 0 && m % 5 == 0) { push(5); m /= 5; }
@@ -133,9 +137,9 @@ extern "C" int64_t pdhg_launch_count(const pdhg_handle* h) { return h ? h->launc
 
 static void fill_params(pdhg_handle* h, MarchParams* p);
 
-extern "C" int pdhg_phase_times(pdhg_handle* h, double* out6) {
+extern "C" int pdhg_phase_times(pdhg_handle* h, double* out6 /* 16 doubles */) {
   if (!h || !out6) return fail(PDHG_ERR_ARG, "pdhg_phase_times: null argument");
-  if (h->path != 2) { for (int i = 0; i < 6; ++i) out6[i] = 0.0; return PDHG_OK; }
+  if (h->path != 2) { for (int i = 0; i < 16; ++i) out6[i] = 0.0; return PDHG_OK; }
   MarchParams p;
   fill_params(h, &p);
   CU(cudaSetDevice(h->cfg.device));

@@ -23,7 +23,14 @@ namespace cg = cooperative_groups;
 namespace pdhg {
 
 constexpr int kNQ = 20;        // reduced quantities per epoch
-constexpr int kThreads = 512;
+#ifndef PDHG_COOP_THREADS
+#define PDHG_COOP_THREADS 512
+#endif
+#ifndef PDHG_COOP_CTAS_PER_SM
+#define PDHG_COOP_CTAS_PER_SM 1
+#endif
+constexpr int kThreads = PDHG_COOP_THREADS;
+constexpr int kCtasPerSm = PDHG_COOP_CTAS_PER_SM;
 constexpr int kWarps = kThreads / 32;
 
 struct CoopWs {
@@ -75,7 +82,17 @@ struct Ctx {
   double2* work;        // FFT buffers
   double* red;          // [kNQ*kWarps] static scratch
   int epoch;
+  unsigned long long tsub[10], tl;   // diagnostic sub-phase timers (CTA 0, thread 0 only)
+  __device__ __forceinline__ void tick(int slot) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      tsub[slot] += t - tl; tl = t;
+    }
+  }
   __device__ Ctx(const CoopArgs& a_, double2* sm, double* red_) : a(a_), grid(cg::this_grid()), red(red_), epoch(0) {
+    for (int i = 0; i < 10; ++i) tsub[i] = 0;
+    tl = 0;
     double2* tx = sm;
     double2* ty = tx + a.nxe;
     double* px = reinterpret_cast<double*>(ty + a.nye);
@@ -202,7 +219,7 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
   const int K = p.K, nx = a.nxe, ny = a.nye, nyh = a.nyh, TR = a.TR;
   const size_t n = (size_t)nx * ny, KN = (size_t)K * n;
   const int rows = K * nx, ntiles = (rows + TR - 1) / TR;
-  const int ld = ny + 1;
+  const int ld = fft_ld(ny);
   double2* buf0 = c.work;
   double2* buf1 = buf0 + (size_t)(TR / 2) * ld;
   const double* rho = a.w.rho[cd];
@@ -269,18 +286,20 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
                                     epsl, rc, c_dt);
         }
       }
-      double* dst = reinterpret_cast<double*>(&buf0[(size_t)(lr >> 1) * ld + j]) + (lr & 1);
+      double* dst = reinterpret_cast<double*>(&buf0[(size_t)(lr >> 1) * ld + fpad(j)]) + (lr & 1);
 #pragma unroll
       for (int e = 0; e < VW; ++e) dst[2 * e] = res.e[e];
       lr += dlr; jp += djp;
       if (jp >= ny2) { jp -= ny2; ++lr; }
     }
     __syncthreads();
+    c.tick(0);
     double2* zf = fft_rows(buf0, buf1, a.plan_ye, ld, c.twy, npairs, 1.0);
+    c.tick(1);
     for (int idx = tid; idx < npairs * nyh; idx += nth) {
       const int ky = idx / npairs, pr = idx - ky * npairs;
       const int kym = (ky == 0) ? 0 : ny - ky;
-      const double2 z1 = zf[(size_t)pr * ld + ky], z2 = zf[(size_t)pr * ld + kym];
+      const double2 z1 = zf[(size_t)pr * ld + fpad(ky)], z2 = zf[(size_t)pr * ld + fpad(kym)];
       const int ra = r0 + 2 * pr, ka = ra / nx, ia = ra - ka * nx;
       a.w.zt[((size_t)ka * nyh + ky) * nx + ia] = make_double2(0.5 * (z1.x + z2.x), 0.5 * (z1.y - z2.y));
       if (2 * pr + 1 < nrows) {
@@ -289,6 +308,7 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
       }
     }
     __syncthreads();
+    c.tick(2);
   }
 }
 
@@ -349,7 +369,7 @@ __device__ __noinline__ void phase_B(Ctx& c) {
     }
     return;
   }
-  const int ld = nx + 1;
+  const int ld = fft_ld(nx);
   const int TKY = a.TKY;
   double2* buf0 = c.work;
   double2* buf1 = buf0 + (size_t)TKY * ld;
@@ -361,7 +381,7 @@ __device__ __noinline__ void phase_B(Ctx& c) {
     const int nr = min(TKY, nyh - ky0);
     for (int idx = tid; idx < nr * nx; idx += nth) {
       const int t = idx / nx, kx = idx - t * nx;
-      buf0[(size_t)t * ld + kx] = zt[((size_t)k * nyh + ky0 + t) * nx + kx];
+      buf0[(size_t)t * ld + fpad(kx)] = zt[((size_t)k * nyh + ky0 + t) * nx + kx];
     }
     __syncthreads();
     double2* zf = fft_rows(buf0, buf1, a.plan_xe, ld, c.twx, nr, 1.0);
@@ -370,37 +390,39 @@ __device__ __noinline__ void phase_B(Ctx& c) {
       for (int idx = tid; idx < nr * nx; idx += nth) {
         const int t = idx / nx, kx = idx - t * nx;
         const double rd = 1.0 / (p.diag[(size_t)kx * nyh + ky0 + t] + ((K == 1) ? ct2 : 0.0));
-        const double2 v = zf[(size_t)t * ld + kx];
-        zf[(size_t)t * ld + kx] = make_double2(v.x * rd, v.y * rd);
+        const double2 v = zf[(size_t)t * ld + fpad(kx)];
+        zf[(size_t)t * ld + fpad(kx)] = make_double2(v.x * rd, v.y * rd);
       }
       __syncthreads();
       zf = fft_rows(zf, zo, a.plan_xe, ld, c.twx, nr, -1.0);
     }
     for (int idx = tid; idx < nr * nx; idx += nth) {
       const int t = idx / nx, kx = idx - t * nx;
-      zt[((size_t)k * nyh + ky0 + t) * nx + kx] = zf[(size_t)t * ld + kx];
+      zt[((size_t)k * nyh + ky0 + t) * nx + kx] = zf[(size_t)t * ld + fpad(kx)];
     }
     __syncthreads();
   }
   if (!coupled) return;
   c.grid.sync();
+  c.tick(3);
   // pass 2: Thomas over k, one thread per real component of a mode (coalesced across modes)
   for (size_t w = (size_t)blockIdx.x * nth + tid; w < 2 * modes; w += (size_t)gridDim.x * nth)
     thomas_component(reinterpret_cast<double*>(zt), a.w.den, a.w.tu, K, 2 * modes, w, ct2);
   c.grid.sync();
+  c.tick(4);
   // pass 3: inverse x-FFT of every row
   for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
     const int k = u / ntile, ky0 = (u - k * ntile) * TKY;
     const int nr = min(TKY, nyh - ky0);
     for (int idx = tid; idx < nr * nx; idx += nth) {
       const int t = idx / nx, kx = idx - t * nx;
-      buf0[(size_t)t * ld + kx] = zt[((size_t)k * nyh + ky0 + t) * nx + kx];
+      buf0[(size_t)t * ld + fpad(kx)] = zt[((size_t)k * nyh + ky0 + t) * nx + kx];
     }
     __syncthreads();
     double2* zu = fft_rows(buf0, buf1, a.plan_xe, ld, c.twx, nr, -1.0);
     for (int idx = tid; idx < nr * nx; idx += nth) {
       const int t = idx / nx, kx = idx - t * nx;
-      zt[((size_t)k * nyh + ky0 + t) * nx + kx] = zu[(size_t)t * ld + kx];
+      zt[((size_t)k * nyh + ky0 + t) * nx + kx] = zu[(size_t)t * ld + fpad(kx)];
     }
     __syncthreads();
   }
@@ -414,7 +436,7 @@ __device__ __noinline__ void phase_C(Ctx& c, const double* phi_prev, double* phi
   const int K = p.K, nx = a.nxe, ny = a.nye, nyh = a.nyh, TR = a.TR;
   const size_t n = (size_t)nx * ny;
   const int rows = K * nx, ntiles = (rows + TR - 1) / TR;
-  const int ld = ny + 1;
+  const int ld = fft_ld(ny);
   double2* buf0 = c.work;
   double2* buf1 = buf0 + (size_t)(TR / 2) * ld;
   const int tid = threadIdx.x, nth = blockDim.x;
@@ -434,18 +456,20 @@ __device__ __noinline__ void phase_C(Ctx& c, const double* phi_prev, double* phi
         const int rb = ra + 1, kb = rb / nx, ib = rb - kb * nx;
         ub = a.w.zt[((size_t)kb * nyh + ky) * nx + ib];
       }
-      buf0[(size_t)pr * ld + ky] = make_double2(ua.x - ub.y, ua.y + ub.x);
+      buf0[(size_t)pr * ld + fpad(ky)] = make_double2(ua.x - ub.y, ua.y + ub.x);
       const int kym = ny - ky;
-      if (ky != 0 && kym != ky) buf0[(size_t)pr * ld + kym] = make_double2(ua.x + ub.y, ub.x - ua.y);
+      if (ky != 0 && kym != ky) buf0[(size_t)pr * ld + fpad(kym)] = make_double2(ua.x + ub.y, ub.x - ua.y);
     }
     __syncthreads();
+    c.tick(6);
     double2* zu = fft_rows(buf0, buf1, a.plan_ye, ld, c.twy, npairs, -1.0);
+    c.tick(7);
     int lr = tid / ny2, jp = tid - lr * ny2;
     while (lr < nrows) {
       const int j = jp * VW;
       const int r = r0 + lr, k = r / nx, i = r - k * nx;
       const size_t g = (size_t)(k + 1) * n + (size_t)i * ny + j;
-      const double* zsrc = reinterpret_cast<const double*>(&zu[(size_t)(lr >> 1) * ld + j]) + (lr & 1);
+      const double* zsrc = reinterpret_cast<const double*>(&zu[(size_t)(lr >> 1) * ld + fpad(j)]) + (lr & 1);
       const Vec<VW> pp = ldv<VW>(phi_prev + g);
       Vec<VW> pn, pb;
 #pragma unroll
@@ -462,6 +486,7 @@ __device__ __noinline__ void phase_C(Ctx& c, const double* phi_prev, double* phi
       if (jp >= ny2) { jp -= ny2; ++lr; }
     }
     __syncthreads();
+    c.tick(8);
   }
   const double sums[3] = {s_d, s_p, s_n};
   cta_partials<3>(c, sums, 15);
@@ -640,7 +665,7 @@ __device__ void build_tables(const CoopArgs& a) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) pdhg_coop_kernel(const __grid_constant__ CoopArgs a_param) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const __grid_constant__ CoopArgs a_param) {
   extern __shared__ __align__(16) double2 dynsm[];
   __shared__ double red[kNQ * kWarps];
   // the argument block is referenced from the (non-inlined) phase functions; keep it in shared memory so that it is
@@ -713,7 +738,7 @@ __global__ void __launch_bounds__(kThreads, 1) pdhg_coop_kernel(const __grid_con
   long long inner_total = 0;
   const int nt_all = p.nblocks * K + 1;
   unsigned long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = gtimer();
-#define TICK(slot) do { if (lead) { const unsigned long long t_ = gtimer(); tacc[slot] += t_ - tlast; tlast = t_; } } while (0)
+#define TICK(slot) do { if (lead) { const unsigned long long t_ = gtimer(); tacc[slot] += t_ - tlast; tlast = t_; c.tl = t_; } } while (0)
 
   for (int blk = p.blk_begin; blk < p.blk_end && status == ST_OK; ++blk) {
     const size_t lb = (size_t)b * p.nblocks + blk;
@@ -871,6 +896,7 @@ __global__ void __launch_bounds__(kThreads, 1) pdhg_coop_kernel(const __grid_con
     p.stepsz[b] = stepsz;
     p.inner_total[b] = inner_total;
     for (int q = 0; q < 6; ++q) w.phase_ns[q] = (double)tacc[q];
+    for (int q = 0; q < 10; ++q) w.phase_ns[6 + q] = (double)c.tsub[q];
   }
 #undef TICK
 }
@@ -890,15 +916,15 @@ static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   const size_t tab = (size_t)24 * (g.nxe + g.nye) + 16;            // twiddles + coefficient tables
   const size_t cap = smem_cap > tab ? smem_cap - tab : 0;
   int TR = 16;
-  while (TR > 2 && ((rows + TR - 1) / TR < 2 * sm_count || (size_t)TR * (g.nye + 1) * 16 > cap)) TR -= 2;
+  while (TR > 2 && ((rows + TR - 1) / TR < 2 * sm_count || (size_t)TR * fft_ld(g.nye) * 16 > cap)) TR -= 2;
   g.TR = TR;
   int TKY = 8;
-  while (TKY > 1 && ((size_t)p.K * ((g.nyh + TKY - 1) / TKY) < (size_t)2 * sm_count || (size_t)2 * TKY * (g.nxe + 1) * 16 > cap)) TKY -= 1;
+  while (TKY > 1 && ((size_t)p.K * ((g.nyh + TKY - 1) / TKY) < (size_t)2 * sm_count || (size_t)2 * TKY * fft_ld(g.nxe) * 16 > cap)) TKY -= 1;
   g.TKY = TKY;
-  const size_t smA = (size_t)TR * (g.nye + 1) * 16;                 // 2 buffers * TR/2 rows
-  const size_t smB = (g.nxe > 1) ? (size_t)2 * TKY * (g.nxe + 1) * 16 : 0;
+  const size_t smA = (size_t)TR * fft_ld(g.nye) * 16;                 // 2 buffers * TR/2 rows
+  const size_t smB = (g.nxe > 1) ? (size_t)2 * TKY * fft_ld(g.nxe) * 16 : 0;
   g.smem = tab + (smA > smB ? smA : smB);
-  g.grid = sm_count;
+  g.grid = sm_count * kCtasPerSm;
   return g;
 }
 
@@ -938,7 +964,7 @@ static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, 
   if (e != cudaSuccess) return e;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  const CoopGeom g = coop_geom(p, sms, (size_t)smem_cap - 4096);
+  const CoopGeom g = coop_geom(p, sms, ((size_t)smem_cap - 4096) / kCtasPerSm - (kCtasPerSm > 1 ? 2048 : 0));
   if (g.smem > (size_t)smem_cap - 2048) return cudaErrorInvalidConfiguration;
   CoopArgs a;
   memset(&a, 0, sizeof(a));
@@ -970,7 +996,7 @@ static cudaError_t ensure_tables(const MarchParams& p, void* ws, cudaStream_t st
 
 cudaError_t coop_phase_times(const MarchParams& p, void* ws, double* out6) {
   const CoopWs w = carve(p, ws);
-  return cudaMemcpy(out6, w.phase_ns, 6 * sizeof(double), cudaMemcpyDeviceToHost);
+  return cudaMemcpy(out6, w.phase_ns, 16 * sizeof(double), cudaMemcpyDeviceToHost);
 }
 
 cudaError_t launch_pdhg_coop(const MarchParams& p, int B, void* ws, cudaStream_t stream, long long* launches) {

@@ -27,98 +27,202 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 }
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-// multiply by -i*sg  (sg=+1: forward rotation by -i; sg=-1: inverse rotation by +i)
-__device__ __forceinline__ double2 rot_mi(double2 a, double sg) { return make_double2(sg * a.y, -sg * a.x); }
 
-// One Stockham autosort stage over `rows` independent rows of length n (row stride `ld` complex elements).
+// Exact floor(w / d) for 0 <= w < 2^21 through a float reciprocal (a runtime 32-bit division is a ~150-cycle
+// dependent chain on the critical path of every latency-bound FFT stage).
+__device__ __forceinline__ int fast_div(int w, float inv_d) { return __float2int_rz(((float)w + 0.5f) * inv_d); }
+
+// Shared-memory rows are stored with one pad element per 16 (conflict-free 16-byte accesses for the strided
+// stores of the first Stockham stage and the unit-stride loads of the later ones).
+__device__ __forceinline__ int fpad(int e) { return e + (e >> 4); }
+__host__ __device__ __forceinline__ int fft_ld(int n) { return n + (n >> 4) + 1; }
+
+// ---- in-register DFTs of size R (natural order in, natural order out); INV flips the sign of the exponent ----
+template <bool INV> __device__ __forceinline__ double2 mul_mi(double2 a) {   // a * (-i) forward, a * (+i) inverse
+  return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+}
+template <bool INV> __device__ __forceinline__ double2 mul_w(double2 a, double c, double s) {   // a * (c - i s) fwd, (c + i s) inv
+  return INV ? make_double2(a.x * c - a.y * s, a.y * c + a.x * s) : make_double2(a.x * c + a.y * s, a.y * c - a.x * s);
+}
+template <bool INV> __device__ __forceinline__ void dft4(double2& x0, double2& x1, double2& x2, double2& x3) {
+  const double2 t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = mul_mi<INV>(csub(x1, x3));
+  x0 = cadd(t0, t2); x1 = cadd(t1, t3); x2 = csub(t0, t2); x3 = csub(t1, t3);
+}
+template <int R, bool INV> struct Dft;
+template <bool INV> struct Dft<2, INV> {
+  static __device__ __forceinline__ void run(double2 (&v)[2]) { const double2 a = v[0]; v[0] = cadd(a, v[1]); v[1] = csub(a, v[1]); }
+};
+template <bool INV> struct Dft<4, INV> {
+  static __device__ __forceinline__ void run(double2 (&v)[4]) { dft4<INV>(v[0], v[1], v[2], v[3]); }
+};
+template <bool INV> struct Dft<3, INV> {
+  static __device__ __forceinline__ void run(double2 (&v)[3]) {
+    const double h = 0.86602540378443864676;
+    const double2 p = cadd(v[1], v[2]), m = csub(v[1], v[2]);
+    const double2 e = make_double2(v[0].x - 0.5 * p.x, v[0].y - 0.5 * p.y);
+    const double2 o = mul_mi<INV>(make_double2(h * m.x, h * m.y));
+    v[0] = cadd(v[0], p); v[1] = cadd(e, o); v[2] = csub(e, o);
+  }
+};
+template <bool INV> struct Dft<5, INV> {
+  static __device__ __forceinline__ void run(double2 (&v)[5]) {
+    const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;   // cos(2pi/5), cos(4pi/5)
+    const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;    // sin(2pi/5), sin(4pi/5)
+    const double2 a0 = v[0];
+    const double2 p14 = cadd(v[1], v[4]), m14 = csub(v[1], v[4]), p23 = cadd(v[2], v[3]), m23 = csub(v[2], v[3]);
+    const double2 e1 = make_double2(a0.x + c1 * p14.x + c2 * p23.x, a0.y + c1 * p14.y + c2 * p23.y);
+    const double2 e2 = make_double2(a0.x + c2 * p14.x + c1 * p23.x, a0.y + c2 * p14.y + c1 * p23.y);
+    const double2 o1 = mul_mi<INV>(make_double2(s1 * m14.x + s2 * m23.x, s1 * m14.y + s2 * m23.y));
+    const double2 o2 = mul_mi<INV>(make_double2(s2 * m14.x - s1 * m23.x, s2 * m14.y - s1 * m23.y));
+    v[0] = make_double2(a0.x + p14.x + p23.x, a0.y + p14.y + p23.y);
+    v[1] = cadd(e1, o1); v[4] = csub(e1, o1); v[2] = cadd(e2, o2); v[3] = csub(e2, o2);
+  }
+};
+template <bool INV> struct Dft<8, INV> {
+  // 2 x 4: radix-2 over (b, b+4), twiddle W8^b on the odd half, then two radix-4
+  static __device__ __forceinline__ void run(double2 (&v)[8]) {
+    const double r = 0.70710678118654752440;
+    double2 e[4], o[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { e[b] = cadd(v[b], v[b + 4]); o[b] = csub(v[b], v[b + 4]); }
+    o[1] = mul_w<INV>(o[1], r, r);
+    o[2] = mul_mi<INV>(o[2]);
+    o[3] = mul_w<INV>(o[3], -r, r);
+    dft4<INV>(e[0], e[1], e[2], e[3]);
+    dft4<INV>(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { v[2 * c] = e[c]; v[2 * c + 1] = o[c]; }
+  }
+};
+template <bool INV> struct Dft<16, INV> {
+  // 4 x 4: radix-4 over (b, b+4, b+8, b+12) -> u[b][a]; u[b][a] *= W16^(a b); radix-4 over b -> X[a + 4 c]
+  static __device__ __forceinline__ void run(double2 (&v)[16]) {
+    const double c8 = 0.92387953251128675613, s8 = 0.38268343236508977173, r = 0.70710678118654752440;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) dft4<INV>(v[b], v[b + 4], v[b + 8], v[b + 12]);     // v[b + 4a] = u[b][a]
+    v[1 + 4] = mul_w<INV>(v[1 + 4], c8, s8);    // W16^1
+    v[1 + 8] = mul_w<INV>(v[1 + 8], r, r);      // W16^2
+    v[1 + 12] = mul_w<INV>(v[1 + 12], s8, c8);  // W16^3
+    v[2 + 4] = mul_w<INV>(v[2 + 4], r, r);      // W16^2
+    v[2 + 8] = mul_mi<INV>(v[2 + 8]);           // W16^4
+    v[2 + 12] = mul_w<INV>(v[2 + 12], -r, r);   // W16^6
+    v[3 + 4] = mul_w<INV>(v[3 + 4], s8, c8);    // W16^3
+    v[3 + 8] = mul_w<INV>(v[3 + 8], -r, r);     // W16^6
+    v[3 + 12] = mul_w<INV>(v[3 + 12], -c8, -s8);  // W16^9 = -W16^1
+#pragma unroll
+    for (int a = 0; a < 4; ++a) dft4<INV>(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3]);   // -> X[a + 4c] at v[4a + c]
+    // reorder v[4a + c] -> X[a + 4c]
+    double2 t[16];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) t[a + 4 * c] = v[4 * a + c];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = t[i];
+  }
+};
+
+// One Stockham autosort stage over `rows` independent rows of length n (row stride `ld` complex elements, padded
+// element addressing fpad()).
 //   src[j + t*n/R] * w^(t*k)  --radix-R DFT-->  dst[(j-k)*R + k + t*Ns],   k = j mod Ns,  w = exp(-+2*pi*i/(Ns*R))
-// tw[m] = exp(-2*pi*i*m/n) is the master twiddle table (host-computed); sg = +1 forward, -1 inverse (unnormalised).
+// tw[m] = exp(-2*pi*i*m/n) is the master twiddle table; INV = false forward, true inverse (unnormalised).
+template <int R, bool INV>
 __device__ __forceinline__ void fft_stage(const double2* __restrict__ src, double2* __restrict__ dst, int n, int ld,
-                                          int R, int Ns, const double2* __restrict__ tw, int rows, double sg,
-                                          int tid, int nthreads) {
+                                          int Ns, const double2* __restrict__ tw, int rows, int tid, int nthreads) {
   const int nb = n / R;
-  const int twstep = n / (Ns * R);
+  const int twstep = nb / Ns;
   const int total = rows * nb;
+  const float inv_nb = 1.0f / (float)nb, inv_ns = 1.0f / (float)Ns;
+  const bool ns_pow2 = (Ns & (Ns - 1)) == 0;
   for (int w = tid; w < total; w += nthreads) {
-    const int row = w / nb;
+    const int row = (rows == 1) ? 0 : fast_div(w, inv_nb);
     const int j = w - row * nb;
-    const int k = j % Ns;
-    const double2* s = src + (size_t)row * ld + j;
-    double2* d = dst + (size_t)row * ld + (j - k) * R + k;
-    if (R == 4) {
-      double2 a0 = s[0], a1 = s[nb], a2 = s[2 * nb], a3 = s[3 * nb];
-      if (k) {
-        double2 w1 = tw[k * twstep], w2 = tw[2 * k * twstep], w3 = tw[3 * k * twstep];
-        w1.y *= sg; w2.y *= sg; w3.y *= sg;
-        a1 = cmul(a1, w1); a2 = cmul(a2, w2); a3 = cmul(a3, w3);
+    const int k = ns_pow2 ? (j & (Ns - 1)) : (j - fast_div(j, inv_ns) * Ns);
+    const double2* s = src + row * ld;
+    double2* d = dst + row * ld;
+    double2 v[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) v[t] = s[fpad(j + t * nb)];
+    if (Ns > 1) {
+      // external twiddles w^(t k): table loads for t < 4 and t = 4, 8, 12; products for the rest (radix 8/16)
+      const int m1 = k * twstep;
+      double2 wb[4];
+      wb[0] = make_double2(1.0, 0.0);
+#pragma unroll
+      for (int t = 1; t < 4; ++t) {
+        if (t < R) { wb[t] = tw[t * m1]; if (INV) wb[t].y = -wb[t].y; }
       }
-      double2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = rot_mi(csub(a1, a3), sg);
-      d[0] = cadd(t0, t2); d[Ns] = cadd(t1, t3); d[2 * Ns] = csub(t0, t2); d[3 * Ns] = csub(t1, t3);
-    } else if (R == 2) {
-      double2 a0 = s[0], a1 = s[nb];
-      if (k) { double2 w1 = tw[k * twstep]; w1.y *= sg; a1 = cmul(a1, w1); }
-      d[0] = cadd(a0, a1); d[Ns] = csub(a0, a1);
-    } else if (R == 5) {
-      double2 a0 = s[0], a1 = s[nb], a2 = s[2 * nb], a3 = s[3 * nb], a4 = s[4 * nb];
-      if (k) {
-        double2 w1 = tw[k * twstep], w2 = tw[2 * k * twstep], w3 = tw[3 * k * twstep], w4 = tw[4 * k * twstep];
-        w1.y *= sg; w2.y *= sg; w3.y *= sg; w4.y *= sg;
-        a1 = cmul(a1, w1); a2 = cmul(a2, w2); a3 = cmul(a3, w3); a4 = cmul(a4, w4);
-      }
-      const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;   // cos(2pi/5), cos(4pi/5)
-      const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;    // sin(2pi/5), sin(4pi/5)
-      double2 p14 = cadd(a1, a4), m14 = csub(a1, a4), p23 = cadd(a2, a3), m23 = csub(a2, a3);
-      double2 e1 = make_double2(a0.x + c1 * p14.x + c2 * p23.x, a0.y + c1 * p14.y + c2 * p23.y);
-      double2 e2 = make_double2(a0.x + c2 * p14.x + c1 * p23.x, a0.y + c2 * p14.y + c1 * p23.y);
-      double2 o1 = rot_mi(make_double2(s1 * m14.x + s2 * m23.x, s1 * m14.y + s2 * m23.y), sg);
-      double2 o2 = rot_mi(make_double2(s2 * m14.x - s1 * m23.x, s2 * m14.y - s1 * m23.y), sg);
-      d[0] = make_double2(a0.x + p14.x + p23.x, a0.y + p14.y + p23.y);
-      d[Ns] = cadd(e1, o1); d[4 * Ns] = csub(e1, o1);
-      d[2 * Ns] = cadd(e2, o2); d[3 * Ns] = csub(e2, o2);
-    } else if (R == 3) {
-      double2 a0 = s[0], a1 = s[nb], a2 = s[2 * nb];
-      if (k) {
-        double2 w1 = tw[k * twstep], w2 = tw[2 * k * twstep];
-        w1.y *= sg; w2.y *= sg;
-        a1 = cmul(a1, w1); a2 = cmul(a2, w2);
-      }
-      const double h = 0.86602540378443864676;   // sqrt(3)/2
-      double2 p = cadd(a1, a2), m = csub(a1, a2);
-      double2 e = make_double2(a0.x - 0.5 * p.x, a0.y - 0.5 * p.y);
-      double2 o = rot_mi(make_double2(h * m.x, h * m.y), sg);
-      d[0] = cadd(a0, p); d[Ns] = cadd(e, o); d[2 * Ns] = csub(e, o);
-    } else {
-      // generic radix (any other prime factor): out[q] = sum_t src[t] * w^(t*k) * W_R^(t*q)
-      const int rstep = n / R;
-      for (int q = 0; q < R; ++q) {
-        double2 acc = make_double2(0.0, 0.0);
-        for (int t = 0; t < R; ++t) {
-          double2 v = s[t * nb];
-          int m = (int)(((long long)t * k * twstep + (long long)((t * q) % R) * rstep) % n);
-          double2 ww = tw[m]; ww.y *= sg;
-          acc = cadd(acc, cmul(v, ww));
+#pragma unroll
+      for (int t = 1; t < 4; ++t) if (t < R) v[t] = cmul(v[t], wb[t]);
+#pragma unroll
+      for (int a = 1; a < 4; ++a) {
+        if (4 * a < R) {
+          double2 wa = tw[4 * a * m1];
+          if (INV) wa.y = -wa.y;
+          v[4 * a] = cmul(v[4 * a], wa);
+#pragma unroll
+          for (int t = 1; t < 4; ++t) if (4 * a + t < R) v[4 * a + t] = cmul(v[4 * a + t], cmul(wa, wb[t]));
         }
-        d[q * Ns] = acc;
       }
+    }
+    Dft<R, INV>::run(v);
+    const int base = (j - k) * R + k;
+#pragma unroll
+    for (int q = 0; q < R; ++q) d[fpad(base + q * Ns)] = v[q];
+  }
+}
+
+// generic radix (any other prime factor): out[q] = sum_t src[t] * w^(t*k) * W_R^(t*q)
+template <bool INV>
+__device__ __noinline__ void fft_stage_generic(const double2* src, double2* dst, int n, int ld, int R, int Ns, const double2* tw,
+                                               int rows, int tid, int nthreads) {
+  const int nb = n / R, twstep = nb / Ns, rstep = n / R;
+  for (int w = tid; w < rows * nb; w += nthreads) {
+    const int row = w / nb, j = w - row * nb, k = j % Ns;
+    const double2* s = src + row * ld;
+    double2* d = dst + row * ld;
+    for (int q = 0; q < R; ++q) {
+      double2 acc = make_double2(0.0, 0.0);
+      for (int t = 0; t < R; ++t) {
+        const double2 v = s[fpad(j + t * nb)];
+        const int m = (int)(((long long)t * k * twstep + (long long)((t * q) % R) * rstep) % n);
+        double2 ww = tw[m];
+        if (INV) ww.y = -ww.y;
+        acc = cadd(acc, cmul(v, ww));
+      }
+      d[fpad((j - k) * R + k + q * Ns)] = acc;
     }
   }
 }
 
-// Full transform of `rows` rows held in buf0; ping-pongs with buf1; returns the buffer that holds the result.
-// All threads of the CTA must call it; it ends with a __syncthreads().
-__device__ __forceinline__ double2* fft_rows(double2* buf0, double2* buf1, const FftPlan& plan, int ld,
-                                             const double2* __restrict__ tw, int rows, double sg) {
+// Full transform of `rows` rows held in buf0 (padded addressing, row stride ld >= fft_ld(n)); ping-pongs with buf1;
+// returns the buffer that holds the result.  All threads of the CTA must call it; it ends with a __syncthreads().
+template <bool INV>
+__device__ __forceinline__ double2* fft_rows_dir(double2* buf0, double2* buf1, const FftPlan& plan, int ld,
+                                                 const double2* __restrict__ tw, int rows) {
   int Ns = 1;
   double2* a = buf0;
   double2* b = buf1;
+  const int tid = threadIdx.x, nth = blockDim.x, n = plan.n;
   for (int s = 0; s < plan.nstages; ++s) {
     const int R = plan.radix[s];
-    fft_stage(a, b, plan.n, ld, R, Ns, tw, rows, sg, threadIdx.x, blockDim.x);
+    if (R == 16) fft_stage<16, INV>(a, b, n, ld, Ns, tw, rows, tid, nth);
+    else if (R == 8) fft_stage<8, INV>(a, b, n, ld, Ns, tw, rows, tid, nth);
+    else if (R == 4) fft_stage<4, INV>(a, b, n, ld, Ns, tw, rows, tid, nth);
+    else if (R == 2) fft_stage<2, INV>(a, b, n, ld, Ns, tw, rows, tid, nth);
+    else if (R == 5) fft_stage<5, INV>(a, b, n, ld, Ns, tw, rows, tid, nth);
+    else if (R == 3) fft_stage<3, INV>(a, b, n, ld, Ns, tw, rows, tid, nth);
+    else fft_stage_generic<INV>(a, b, n, ld, R, Ns, tw, rows, tid, nth);
     __syncthreads();
     Ns *= R;
     double2* t = a; a = b; b = t;
   }
   return a;
+}
+
+__device__ __forceinline__ double2* fft_rows(double2* buf0, double2* buf1, const FftPlan& plan, int ld,
+                                             const double2* __restrict__ tw, int rows, double sg) {
+  return (sg > 0.0) ? fft_rows_dir<false>(buf0, buf1, plan, ld, tw, rows) : fft_rows_dir<true>(buf0, buf1, plan, ld, tw, rows);
 }
 
 // ---------------------------------------------------------------------------------------------------

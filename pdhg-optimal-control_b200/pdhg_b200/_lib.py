@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libpdhg_b200.so")
+LIB_PATH = os.environ.get("PDHG_B200_LIB", os.path.join(os.path.dirname(_HERE), "lib", "libpdhg_b200.so"))
 
 PDHG_OK, PDHG_ERR_ARG, PDHG_ERR_CUDA, PDHG_ERR_NOMEM, PDHG_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 INST_OK, INST_SOL_NAN, INST_PAUSED, INST_LOG_OVERFLOW = 0, 1, 3, 4
@@ -157,9 +157,11 @@ class Solver:
     return float(self.lib.pdhg_last_kernel_ms(self._h))
 
   def phase_times_ms(self):
-    out = np.zeros(6)
+    out = np.zeros(16)
     _check(self.lib.pdhg_phase_times(self._h, _hptr(out)))
-    return dict(zip(("A_residual_ffty", "B_fftx_tsolve", "C_iffty_phi", "D_dual_reduce", "unused", "setup_records_output"), (out / 1e6).tolist()))
+    names = ("A_residual_ffty", "B_fftx_tsolve", "C_iffty_phi", "D_dual_reduce", "unused", "setup_records_output",
+             "a_compute", "a_fft", "a_store", "b_pass1", "b_pass2", "b_pass3", "c_load", "c_fft", "c_update", "spare")
+    return dict(zip(names, (out / 1e6).tolist()))
 
   @property
   def launch_count(self):
