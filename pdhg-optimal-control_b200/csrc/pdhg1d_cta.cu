@@ -13,7 +13,7 @@
 
 namespace pdhg {
 
-__global__ void __launch_bounds__(256, 1) pdhg1d_cta_kernel(const MarchParams p) {
+__global__ void __launch_bounds__(256, 2) pdhg1d_cta_kernel(const MarchParams p) {
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, nth = blockDim.x;
   const int b = blockIdx.x;
@@ -45,6 +45,10 @@ __global__ void __launch_bounds__(256, 1) pdhg1d_cta_kernel(const MarchParams p)
   int status = ST_OK;
   int blocks_done = p.blk_begin;
   long long inner_total = 0;
+  // diagnostic cycle counters (instance 0, thread 0): residual, FFT, solve, IFFT, phi update, dual sweeps, decisions
+  long long tc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tl = clock64();
+  const bool prof = (p.dbg_ns != nullptr) && b == 0 && tid == 0;
+#define TCK(slot) do { if (prof) { const long long t_ = clock64(); tc[slot] += t_ - tl; tl = t_; } } while (0)
 
   for (int blk = p.blk_begin; blk < p.blk_end && status == ST_OK; ++blk) {
     const size_t lb = (size_t)b * p.nblocks + blk;
@@ -74,6 +78,7 @@ __global__ void __launch_bounds__(256, 1) pdhg1d_cta_kernel(const MarchParams p)
       for (; it < p.n_maxiter; ++it) {
         if (it >= p.iter_pause) { reason = END_PAUSED; break; }
 
+        TCK(7);
         // ---- continuity residual rows 1..K -> z0 (update_fns_in_pdhg.py:72-81) ----
         for (int i = tid; i < N; i += nth) {
           const int k = i / nx, x = i - k * nx;
@@ -91,9 +96,11 @@ __global__ void __launch_bounds__(256, 1) pdhg1d_cta_kernel(const MarchParams p)
           z0[k * ld + fpad(x)] = make_double2(res, 0.0);
         }
         __syncthreads();
+        TCK(0);
 
         // ---- H1 preconditioner (utils_precond.py:105-140): FFT_x, per-mode t-solve, IFFT_x ----
-        double2* zf = fft_rows(z0, z1, p.plan_x, ld, p.tw_x, K, 1.0);
+        double2* zf = fft_rows<8>(z0, z1, p.plan_1d, ld, p.tw_x, K, 1.0);
+        TCK(1);
         double2* zo = (zf == z0) ? z1 : z0;
         if (K == 1) {
           for (int m = tid; m < nx; m += nth) {
@@ -137,7 +144,9 @@ __global__ void __launch_bounds__(256, 1) pdhg1d_cta_kernel(const MarchParams p)
           }
         }
         __syncthreads();
-        double2* zu = fft_rows(zf, zo, p.plan_x, ld, p.tw_x, K, -1.0);
+        TCK(2);
+        double2* zu = fft_rows<8>(zf, zo, p.plan_1d, ld, p.tw_x, K, -1.0);
+        TCK(3);
 
         // ---- phi_next = phi_prev + tau*u ; phi_bar = 2 phi_next - phi_prev (utils_pdhg_solver.py:53-55) ----
         int nanflag = 0;
@@ -156,6 +165,7 @@ __global__ void __launch_bounds__(256, 1) pdhg1d_cta_kernel(const MarchParams p)
         if (it == p.iter_begin) for (int i = tid; i < nx; i += nth) phib[i] = phi[i];
         block_sum<2>(sp, red);     // (its barriers also order the phib writes before the sweeps below)
         err1 = sqrt(sp[0]) / sqrt(S_row0 + sp[1]);
+        TCK(4);
 
         // ---- dual sweeps (update_fns_in_pdhg.py:150-180) ----
         double v[9];
@@ -199,6 +209,7 @@ __global__ void __launch_bounds__(256, 1) pdhg1d_cta_kernel(const MarchParams p)
           if (err < eps) { ++j; break; }
         }
         inner_total += j;
+        TCK(5);
         const bool multi = (j > 1);
         const double d_rho = multi ? v[6] : v[0], d_a1 = multi ? v[7] : v[2], d_a2 = multi ? v[8] : v[4];
 
@@ -214,6 +225,7 @@ __global__ void __launch_bounds__(256, 1) pdhg1d_cta_kernel(const MarchParams p)
         }
         S_rho = v[1]; S_a1 = v[3]; S_a2 = v[5];
         nanflag = __syncthreads_or(nanflag);
+        TCK(6);
         if (err1 < eps && err2 < eps) { reason = END_CONVERGED; break; }
         if (nanflag) { reason = END_NAN; break; }
         if (p.print_freq > 0 && it % p.print_freq == 0) {
@@ -295,6 +307,8 @@ __global__ void __launch_bounds__(256, 1) pdhg1d_cta_kernel(const MarchParams p)
       break;
     }
   }
+  if (prof) for (int q = 0; q < 8; ++q) p.dbg_ns[q] = (double)tc[q];
+#undef TCK
   if (tid == 0) {
     p.status[b] = status;
     p.blocks_done[b] = blocks_done;

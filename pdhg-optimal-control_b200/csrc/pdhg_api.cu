@@ -50,7 +50,7 @@ struct pdhg_handle {
   std::vector<void*> owned;
   double *coef_x = nullptr, *coef_y = nullptr, *diag = nullptr;
   double2 *tw_x = nullptr, *tw_y = nullptr;
-  FftPlan plan_x{}, plan_y{};
+  FftPlan plan_x{}, plan_y{}, plan_1d{};
   double *epsl = nullptr, *stepsz = nullptr, *delta = nullptr, *floor_ = nullptr;
   double *st_phi = nullptr, *st_rho = nullptr, *st_alp = nullptr;
   long long* iters = nullptr;
@@ -61,6 +61,7 @@ struct pdhg_handle {
   long long* inner_total = nullptr;
   int* n_inner = nullptr;
   double* err_inner = nullptr;
+  double* dbg_ns = nullptr;
   void* ws = nullptr;         // cooperative-kernel workspace
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the solver kernel(s) of the last march on its stream
   bool ev_valid = false;
@@ -81,7 +82,7 @@ static cudaError_t dalloc(pdhg_handle* h, T** p, size_t count) {
 }
 
 static bool make_plan(int n, FftPlan* plan, int max_radix = 16) {
-  if (const char* e = getenv("PDHG_MAX_RADIX")) max_radix = atoi(e);
+  if (const char* e = getenv("PDHG_MAX_RADIX")) { const int m_ = atoi(e); if (m_ < max_radix) max_radix = m_; }
   plan->n = n;
   plan->nstages = 0;
   int m = n;
@@ -139,7 +140,12 @@ static void fill_params(pdhg_handle* h, MarchParams* p);
 
 extern "C" int pdhg_phase_times(pdhg_handle* h, double* out6 /* 16 doubles */) {
   if (!h || !out6) return fail(PDHG_ERR_ARG, "pdhg_phase_times: null argument");
-  if (h->path != 2) { for (int i = 0; i < 16; ++i) out6[i] = 0.0; return PDHG_OK; }
+  if (h->path != 2) {
+    // single-CTA kernel: clock cycles of instance 0 per sub-step (only when PDHG_PROFILE is set)
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpy(out6, h->dbg_ns, 16 * sizeof(double), cudaMemcpyDeviceToHost));
+    return PDHG_OK;
+  }
   MarchParams p;
   fill_params(h, &p);
   CU(cudaSetDevice(h->cfg.device));
@@ -178,6 +184,7 @@ extern "C" int pdhg_create(const pdhg_config* cfg, const double* coef_x, const d
     return fail(PDHG_ERR_UNSUPPORTED, "grid size has too many prime factors for the FFT plan");
   }
   if (c.ndim == 1) { h->plan_y.n = 1; h->plan_y.nstages = 0; }
+  make_plan(c.nx, &h->plan_1d, 8);
   // path selection
   int dev_smem = 0;
   cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device);
@@ -229,6 +236,8 @@ extern "C" int pdhg_create(const pdhg_config* cfg, const double* coef_x, const d
   CB(dalloc(h, &h->status, B)); CB(dalloc(h, &h->blocks_done, B)); CB(dalloc(h, &h->inner_total, B));
   CB(dalloc(h, &h->n_inner, B));
   CB(dalloc(h, &h->err_inner, B));
+  CB(dalloc(h, &h->dbg_ns, 16));
+  CB(cudaMemset(h->dbg_ns, 0, 16 * sizeof(double)));
   if (c.ndim == 2 && c.n_ctrl > 1) CB(dalloc(h, &h->alp_tmp, B * h->A * c.K * h->n * c.n_ctrl));
   {
     // the cooperative kernel also serves the operator-level entry points, so its workspace always exists
@@ -256,9 +265,10 @@ static void fill_params(pdhg_handle* h, MarchParams* p) {
   p->epsl = h->epsl; p->stepsz = h->stepsz; p->stepsz_delta = h->delta; p->stepsz_floor = h->floor_;
   p->coef_x = h->coef_x; p->coef_y = h->coef_y; p->diag = h->diag; p->tw_x = h->tw_x; p->tw_y = h->tw_y;
   p->Ct_over_dt2 = (c.ndim == 1 ? c.Ct : 1.0) / (c.dt * c.dt);
-  p->plan_x = h->plan_x; p->plan_y = h->plan_y;
+  p->plan_x = h->plan_x; p->plan_y = h->plan_y; p->plan_1d = h->plan_1d;
   p->st_phi = h->st_phi; p->st_rho = h->st_rho; p->st_alp = h->st_alp;
   p->iters = h->iters; p->stepsz_used = h->stepsz_used; p->nrec = h->nrec; p->errlog = h->errlog;
+  p->dbg_ns = getenv("PDHG_PROFILE") ? h->dbg_ns : nullptr;
   p->end_reason = h->end_reason; p->status = h->status; p->blocks_done = h->blocks_done; p->inner_total = h->inner_total;
 }
 

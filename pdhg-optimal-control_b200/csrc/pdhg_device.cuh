@@ -197,7 +197,7 @@ __device__ __noinline__ void fft_stage_generic(const double2* src, double2* dst,
 
 // Full transform of `rows` rows held in buf0 (padded addressing, row stride ld >= fft_ld(n)); ping-pongs with buf1;
 // returns the buffer that holds the result.  All threads of the CTA must call it; it ends with a __syncthreads().
-template <bool INV>
+template <bool INV, int MAXR>
 __device__ __forceinline__ double2* fft_rows_dir(double2* buf0, double2* buf1, const FftPlan& plan, int ld,
                                                  const double2* __restrict__ tw, int rows) {
   int Ns = 1;
@@ -206,8 +206,8 @@ __device__ __forceinline__ double2* fft_rows_dir(double2* buf0, double2* buf1, c
   const int tid = threadIdx.x, nth = blockDim.x, n = plan.n;
   for (int s = 0; s < plan.nstages; ++s) {
     const int R = plan.radix[s];
-    if (R == 16) fft_stage<16, INV>(a, b, n, ld, Ns, tw, rows, tid, nth);
-    else if (R == 8) fft_stage<8, INV>(a, b, n, ld, Ns, tw, rows, tid, nth);
+    if (MAXR >= 16 && R == 16) fft_stage<16, INV>(a, b, n, ld, Ns, tw, rows, tid, nth);
+    else if (MAXR >= 8 && R == 8) fft_stage<8, INV>(a, b, n, ld, Ns, tw, rows, tid, nth);
     else if (R == 4) fft_stage<4, INV>(a, b, n, ld, Ns, tw, rows, tid, nth);
     else if (R == 2) fft_stage<2, INV>(a, b, n, ld, Ns, tw, rows, tid, nth);
     else if (R == 5) fft_stage<5, INV>(a, b, n, ld, Ns, tw, rows, tid, nth);
@@ -220,9 +220,12 @@ __device__ __forceinline__ double2* fft_rows_dir(double2* buf0, double2* buf1, c
   return a;
 }
 
+// MAXR: largest radix the plan may contain (the host builds the plan accordingly); bounds the register footprint
+template <int MAXR = 16>
 __device__ __forceinline__ double2* fft_rows(double2* buf0, double2* buf1, const FftPlan& plan, int ld,
                                              const double2* __restrict__ tw, int rows, double sg) {
-  return (sg > 0.0) ? fft_rows_dir<false>(buf0, buf1, plan, ld, tw, rows) : fft_rows_dir<true>(buf0, buf1, plan, ld, tw, rows);
+  return (sg > 0.0) ? fft_rows_dir<false, MAXR>(buf0, buf1, plan, ld, tw, rows)
+                    : fft_rows_dir<true, MAXR>(buf0, buf1, plan, ld, tw, rows);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -45,6 +45,7 @@ struct MarchParams {
   const double2* tw_y;             // [ny]
   double Ct_over_dt2;              // Ct/dt^2 (0 => plain divide, utils_precond.py:134)
   FftPlan plan_x, plan_y;
+  FftPlan plan_1d;                 // x plan restricted to radix <= 8 (single-CTA kernel: 128-register budget)
   // state in/out  (planar, active control components only): phi [B][K+1][n], rho [B][K][n], alp [B][A][K][n]
   double* st_phi;
   double* st_rho;
@@ -62,6 +63,7 @@ struct MarchParams {
   int* status;                     // [B]
   int* blocks_done;                // [B]
   long long* inner_total;          // [B] total dual sweeps executed (statistics)
+  double* dbg_ns;                  // [16] diagnostic: clock cycles per sub-step of instance 0 (single-CTA kernel); may be null
 };
 
 }  // namespace pdhg
