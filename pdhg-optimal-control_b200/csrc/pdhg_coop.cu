@@ -82,6 +82,7 @@ struct Ctx {
   double2* work;        // FFT buffers
   double* red;          // [kNQ*kWarps] static scratch
   int epoch;
+  float inv_nx, inv_nchunk;          // float reciprocals for division-free index math
   unsigned long long tsub[10], tl;   // diagnostic sub-phase timers (CTA 0, thread 0 only)
   __device__ __forceinline__ void tick(int slot) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -93,6 +94,11 @@ struct Ctx {
   __device__ Ctx(const CoopArgs& a_, double2* sm, double* red_) : a(a_), grid(cg::this_grid()), red(red_), epoch(0) {
     for (int i = 0; i < 10; ++i) tsub[i] = 0;
     tl = 0;
+    inv_nx = 1.0f / (float)a.nxe;
+    {
+      const int vw = (a.nye & 1) ? 1 : 2;
+      inv_nchunk = 1.0f / (float)(((a.nye / vw) + 31) >> 5);
+    }
     double2* tx = sm;
     double2* ty = tx + a.nxe;
     double* px = reinterpret_cast<double*>(ty + a.nye);
@@ -244,7 +250,7 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
 #pragma unroll
       for (int e = 0; e < VW; ++e) res.e[e] = 0.0;
       if (lr < nrows) {
-        const int r = r0 + lr, k = r / nx, i = r - k * nx;
+        const int r = r0 + lr, k = fast_div_exact(r, nx, c.inv_nx), i = r - k * nx;
         const size_t o = (size_t)k * n + (size_t)i * ny;
         const int jm = (j == 0) ? ny - 1 : j - 1, jq = (j + VW == ny) ? 0 : j + VW;
         const Vec<VW> r00 = ldv<VW>(rho + o + j);
@@ -296,14 +302,15 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
     c.tick(0);
     double2* zf = fft_rows(buf0, buf1, a.plan_ye, ld, c.twy, npairs, 1.0);
     c.tick(1);
+    const float inv_np = 1.0f / (float)npairs;
     for (int idx = tid; idx < npairs * nyh; idx += nth) {
-      const int ky = idx / npairs, pr = idx - ky * npairs;
+      const int ky = fast_div_exact(idx, npairs, inv_np), pr = idx - ky * npairs;
       const int kym = (ky == 0) ? 0 : ny - ky;
       const double2 z1 = zf[(size_t)pr * ld + fpad(ky)], z2 = zf[(size_t)pr * ld + fpad(kym)];
-      const int ra = r0 + 2 * pr, ka = ra / nx, ia = ra - ka * nx;
+      const int ra = r0 + 2 * pr, ka = fast_div_exact(ra, nx, c.inv_nx), ia = ra - ka * nx;
       a.w.zt[((size_t)ka * nyh + ky) * nx + ia] = make_double2(0.5 * (z1.x + z2.x), 0.5 * (z1.y - z2.y));
       if (2 * pr + 1 < nrows) {
-        const int rb = ra + 1, kb = rb / nx, ib = rb - kb * nx;
+        const int rb = ra + 1, kb = fast_div_exact(rb, nx, c.inv_nx), ib = rb - kb * nx;
         a.w.zt[((size_t)kb * nyh + ky) * nx + ib] = make_double2(0.5 * (z1.y + z2.y), 0.5 * (z2.x - z1.x));
       }
     }
@@ -380,7 +387,7 @@ __device__ __noinline__ void phase_B(Ctx& c) {
     const int k = u / ntile, ky0 = (u - k * ntile) * TKY;
     const int nr = min(TKY, nyh - ky0);
     for (int idx = tid; idx < nr * nx; idx += nth) {
-      const int t = idx / nx, kx = idx - t * nx;
+      const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
       buf0[(size_t)t * ld + fpad(kx)] = zt[((size_t)k * nyh + ky0 + t) * nx + kx];
     }
     __syncthreads();
@@ -388,7 +395,7 @@ __device__ __noinline__ void phase_B(Ctx& c) {
     if (!coupled) {
       double2* zo = (zf == buf0) ? buf1 : buf0;
       for (int idx = tid; idx < nr * nx; idx += nth) {
-        const int t = idx / nx, kx = idx - t * nx;
+        const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
         const double rd = 1.0 / (p.diag[(size_t)kx * nyh + ky0 + t] + ((K == 1) ? ct2 : 0.0));
         const double2 v = zf[(size_t)t * ld + fpad(kx)];
         zf[(size_t)t * ld + fpad(kx)] = make_double2(v.x * rd, v.y * rd);
@@ -397,7 +404,7 @@ __device__ __noinline__ void phase_B(Ctx& c) {
       zf = fft_rows(zf, zo, a.plan_xe, ld, c.twx, nr, -1.0);
     }
     for (int idx = tid; idx < nr * nx; idx += nth) {
-      const int t = idx / nx, kx = idx - t * nx;
+      const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
       zt[((size_t)k * nyh + ky0 + t) * nx + kx] = zf[(size_t)t * ld + fpad(kx)];
     }
     __syncthreads();
@@ -415,13 +422,13 @@ __device__ __noinline__ void phase_B(Ctx& c) {
     const int k = u / ntile, ky0 = (u - k * ntile) * TKY;
     const int nr = min(TKY, nyh - ky0);
     for (int idx = tid; idx < nr * nx; idx += nth) {
-      const int t = idx / nx, kx = idx - t * nx;
+      const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
       buf0[(size_t)t * ld + fpad(kx)] = zt[((size_t)k * nyh + ky0 + t) * nx + kx];
     }
     __syncthreads();
     double2* zu = fft_rows(buf0, buf1, a.plan_xe, ld, c.twx, nr, -1.0);
     for (int idx = tid; idx < nr * nx; idx += nth) {
-      const int t = idx / nx, kx = idx - t * nx;
+      const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
       zt[((size_t)k * nyh + ky0 + t) * nx + kx] = zu[(size_t)t * ld + fpad(kx)];
     }
     __syncthreads();
@@ -447,13 +454,14 @@ __device__ __noinline__ void phase_C(Ctx& c, const double* phi_prev, double* phi
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int r0 = tile * TR;
     const int nrows = min(TR, rows - r0), npairs = (nrows + 1) >> 1;
+    const float inv_np = 1.0f / (float)npairs;
     for (int idx = tid; idx < npairs * nyh; idx += nth) {
-      const int ky = idx / npairs, pr = idx - ky * npairs;
-      const int ra = r0 + 2 * pr, ka = ra / nx, ia = ra - ka * nx;
+      const int ky = fast_div_exact(idx, npairs, inv_np), pr = idx - ky * npairs;
+      const int ra = r0 + 2 * pr, ka = fast_div_exact(ra, nx, c.inv_nx), ia = ra - ka * nx;
       const double2 ua = a.w.zt[((size_t)ka * nyh + ky) * nx + ia];
       double2 ub = make_double2(0.0, 0.0);
       if (2 * pr + 1 < nrows) {
-        const int rb = ra + 1, kb = rb / nx, ib = rb - kb * nx;
+        const int rb = ra + 1, kb = fast_div_exact(rb, nx, c.inv_nx), ib = rb - kb * nx;
         ub = a.w.zt[((size_t)kb * nyh + ky) * nx + ib];
       }
       buf0[(size_t)pr * ld + fpad(ky)] = make_double2(ua.x - ub.y, ua.y + ub.x);
@@ -467,7 +475,7 @@ __device__ __noinline__ void phase_C(Ctx& c, const double* phi_prev, double* phi
     int lr = tid / ny2, jp = tid - lr * ny2;
     while (lr < nrows) {
       const int j = jp * VW;
-      const int r = r0 + lr, k = r / nx, i = r - k * nx;
+      const int r = r0 + lr, k = fast_div_exact(r, nx, c.inv_nx), i = r - k * nx;
       const size_t g = (size_t)(k + 1) * n + (size_t)i * ny + j;
       const double* zsrc = reinterpret_cast<const double*>(&zu[(size_t)(lr >> 1) * ld + fpad(j)]) + (lr & 1);
       const Vec<VW> pp = ldv<VW>(phi_prev + g);
@@ -549,10 +557,11 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
 #pragma unroll
   for (int q = 0; q < NA; ++q) { s_da[q] = 0.0; s_aa[q] = 0.0; s_oa[q] = 0.0; }
   for (long long unit = (long long)blockIdx.x * nwarp + (threadIdx.x >> 5); unit < units; unit += (long long)gridDim.x * nwarp) {
-    const int r = (int)(unit / nchunk), ch = (int)(unit - (long long)r * nchunk);
+    const int r = (units < (1LL << 24)) ? fast_div_exact((int)unit, nchunk, c.inv_nchunk) : (int)(unit / nchunk);
+    const int ch = (int)(unit - (long long)r * nchunk);
     const int jp = ch * 32 + lane;
     if (jp >= ny2) continue;
-    const int k = r / nx, i = r - k * nx, j = jp * VW;
+    const int k = fast_div_exact(r, nx, c.inv_nx), i = r - k * nx, j = jp * VW;
     const size_t row = (size_t)i * ny, g = (size_t)k * n + row + j;
     const double* pb1 = phib + (size_t)(k + 1) * n;
     const int jm = (j == 0) ? ny - 1 : j - 1, jq = (j + VW == ny) ? 0 : j + VW;

@@ -31,6 +31,15 @@ __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_doub
 // Exact floor(w / d) for 0 <= w < 2^21 through a float reciprocal (a runtime 32-bit division is a ~150-cycle
 // dependent chain on the critical path of every latency-bound FFT stage).
 __device__ __forceinline__ int fast_div(int w, float inv_d) { return __float2int_rz(((float)w + 0.5f) * inv_d); }
+// exact floor(w / d) for any 0 <= w < 2^31, d > 0: float estimate + one correction step (w < 2^24), else true division
+__device__ __forceinline__ int fast_div_exact(int w, int d, float inv_d) {
+  if (w >= (1 << 24)) return w / d;
+  int q = __float2int_rz((float)w * inv_d);
+  const int r = w - q * d;
+  q += (r >= d) ? 1 : 0;
+  q -= (r < 0) ? 1 : 0;
+  return q;
+}
 
 // Shared-memory rows are stored with one pad element per 16 (conflict-free 16-byte accesses for the strided
 // stores of the first Stockham stage and the unit-stride loads of the later ones).
