@@ -48,7 +48,7 @@ struct pdhg_handle {
   int B = 1;
   long long launches = 0;
   std::vector<void*> owned;
-  double *coef_x = nullptr, *coef_y = nullptr, *diag = nullptr;
+  double *coef_x = nullptr, *coef_y = nullptr, *diag = nullptr, *dct_cos = nullptr;
   double2 *tw_x = nullptr, *tw_y = nullptr;
   FftPlan plan_x{}, plan_y{}, plan_1d{};
   double *epsl = nullptr, *stepsz = nullptr, *delta = nullptr, *floor_ = nullptr;
@@ -108,12 +108,19 @@ static std::vector<double2> make_twiddles(int n) {
 }
 
 // lambda_k = (2 - 2 cos(2 pi k/n))/h^2 = 4 sin^2(pi k/n)/h^2 : minus the symbol of the periodic 3-point Laplacian
-// (compute_Dxx_fft_fv, utils_precond.py:42-71, closed form per SURVEY.md A.6).  Neumann (bc=1, DCT-II symbol):
-// lambda_k = (2 - 2 cos(pi k/n))/h^2.
-static double lap_symbol(int k, int n, double h, int bc) {
-  long double s = (bc == 1) ? sinl(3.14159265358979323846264338327950288L * k / (2.0L * n))
-                            : sinl(3.14159265358979323846264338327950288L * k / (long double)n);
+// (compute_Dxx_fft_fv, utils_precond.py:42-71, closed form per SURVEY.md A.6).
+static double lap_symbol(int k, int n, double h) {
+  const long double s = sinl(3.14159265358979323846264338327950288L * k / (long double)n);
   return (double)(4.0L * s * s / ((long double)h * (long double)h));
+}
+
+// -fv[kx][ky] for bc = (1, 0): the reference takes the DCT-II (x) and FFT (y) of the PERIODIC stencil
+// (utils_precond.py:57-66), i.e. fv = 2 c_0 (-2/dx^2 - lambda_y) + 2 (c_1 + c_{nx-1})/dx^2, c_i = cos(pi kx (2i+1)/(2 nx)).
+static double neumann_x_symbol(int kx, int nx, double dx, double lambda_y) {
+  const long double PI = 3.14159265358979323846264338327950288L;
+  auto c = [&](int i) { return cosl(PI * kx * (2.0L * i + 1.0L) / (2.0L * nx)); };
+  const long double fv = 2.0L * c(0) * (-2.0L / ((long double)dx * dx) - (long double)lambda_y) + 2.0L * (c(1) + c(nx - 1)) / ((long double)dx * dx);
+  return (double)(-fv);
 }
 
 extern "C" const char* pdhg_last_error(void) { return g_err.c_str(); }
@@ -203,12 +210,14 @@ extern "C" int pdhg_create(const pdhg_config* cfg, const double* coef_x, const d
   // tables
   std::vector<double> diag((size_t)c.nx * h->nyh);
   for (int kx = 0; kx < c.nx; ++kx) {
-    const double lx = lap_symbol(kx, c.nx, c.dx, c.bc_x);
+    const double lx = lap_symbol(kx, c.nx, c.dx);
     if (c.ndim == 1) {
       diag[kx] = pow(lx + c.C, c.pow);                    // utils_precond.py:125-126
     } else {
-      for (int ky = 0; ky < h->nyh; ++ky)
-        diag[(size_t)kx * h->nyh + ky] = lx + lap_symbol(ky, c.ny, c.dy, 0) + c.C;   // :168
+      for (int ky = 0; ky < h->nyh; ++ky) {
+        const double ly = lap_symbol(ky, c.ny, c.dy);
+        diag[(size_t)kx * h->nyh + ky] = ((c.bc_x == 1) ? neumann_x_symbol(kx, c.nx, c.dx, ly) : lx + ly) + c.C;   // :168
+      }
     }
   }
   CB(dalloc(h, &h->diag, diag.size()));
@@ -217,8 +226,13 @@ extern "C" int pdhg_create(const pdhg_config* cfg, const double* coef_x, const d
   CB(cudaMemcpy(h->coef_x, coef_x, c.nx * sizeof(double), cudaMemcpyHostToDevice));
   CB(dalloc(h, &h->coef_y, (size_t)c.ny));
   if (coef_y) CB(cudaMemcpy(h->coef_y, coef_y, c.ny * sizeof(double), cudaMemcpyHostToDevice));
+  if (c.bc_x == 1) {
+    std::vector<double> ct((size_t)4 * c.nx);
+    for (int m = 0; m < 4 * c.nx; ++m) ct[m] = (double)cosl(3.14159265358979323846264338327950288L * m / (2.0L * c.nx));
+    CB(dalloc(h, &h->dct_cos, ct.size()));
+    CB(cudaMemcpy(h->dct_cos, ct.data(), ct.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   {
-    // Neumann-x uses a DCT evaluated through a length-2nx... handled inside the cooperative kernel with its own table
     std::vector<double2> tx = make_twiddles(c.nx);
     CB(dalloc(h, &h->tw_x, tx.size()));
     CB(cudaMemcpy(h->tw_x, tx.data(), tx.size() * sizeof(double2), cudaMemcpyHostToDevice));
@@ -263,7 +277,7 @@ static void fill_params(pdhg_handle* h, MarchParams* p) {
   p->eps = c.eps; p->rho_alp_iters = c.rho_alp_iters;
   p->max_rec = c.max_rec;
   p->epsl = h->epsl; p->stepsz = h->stepsz; p->stepsz_delta = h->delta; p->stepsz_floor = h->floor_;
-  p->coef_x = h->coef_x; p->coef_y = h->coef_y; p->diag = h->diag; p->tw_x = h->tw_x; p->tw_y = h->tw_y;
+  p->coef_x = h->coef_x; p->coef_y = h->coef_y; p->diag = h->diag; p->dct_cos = h->dct_cos; p->tw_x = h->tw_x; p->tw_y = h->tw_y;
   p->Ct_over_dt2 = (c.ndim == 1 ? c.Ct : 1.0) / (c.dt * c.dt);
   p->plan_x = h->plan_x; p->plan_y = h->plan_y; p->plan_1d = h->plan_1d;
   p->st_phi = h->st_phi; p->st_rho = h->st_rho; p->st_alp = h->st_alp;

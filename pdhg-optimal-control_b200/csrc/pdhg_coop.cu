@@ -14,6 +14,7 @@
 // followed by one grid reduction that drives the inner early exit, the convergence / NaN exits, the records and
 // the step-size fallback exactly as utils_pdhg_solver.py:59-80,174-187 do on the host.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "pdhg_params.h"
@@ -57,6 +58,7 @@ struct CoopArgs {
   int nyh;            // nye/2 + 1
   int TR, TKY;        // rows per y-FFT tile (even), ky rows per x-FFT tile
   int has_x;          // 0 for a 1-D problem
+  int d_pipe;         // 1: cp.async-pipelined dual sweep (ny even and the staging buffers fit shared memory)
   double dxe, dye;
   const double* coef_xe;
   const double* coef_ye;
@@ -391,6 +393,42 @@ __device__ __noinline__ void phase_B(Ctx& c) {
       buf0[(size_t)t * ld + fpad(kx)] = zt[((size_t)k * nyh + ky0 + t) * nx + kx];
     }
     __syncthreads();
+    if (p.bc_x == 1) {
+      // Neumann in x (egno 3): DCT-II along x, divide, inverse DCT (utils_precond.py:159-161,172-174), evaluated directly
+      // (O(nx^2) per row; this path only serves the small Newton example and is uncoupled: K = 1)
+      const double* ct = p.dct_cos;
+      const int m4 = 4 * nx;
+      for (int idx = tid; idx < nr * nx; idx += nth) {
+        const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
+        double sx = 0.0, sy = 0.0;
+        int m = kx % m4;                                  // index kx (2 i + 1) mod 4 nx, advanced by 2 kx per i
+        for (int i = 0; i < nx; ++i) {
+          const double2 v = buf0[(size_t)t * ld + fpad(i)];
+          const double cv = ct[m];
+          sx += v.x * cv; sy += v.y * cv;
+          m += 2 * kx; if (m >= m4) m -= m4; if (m >= m4) m -= m4;
+        }
+        const double rd = 1.0 / (p.diag[(size_t)kx * nyh + ky0 + t] + ct2);
+        buf1[(size_t)t * ld + fpad(kx)] = make_double2(2.0 * sx * rd, 2.0 * sy * rd);
+      }
+      __syncthreads();
+      for (int idx = tid; idx < nr * nx; idx += nth) {
+        const int t = fast_div_exact(idx, nx, c.inv_nx), i = idx - t * nx;
+        const double2 y0 = buf1[(size_t)t * ld + fpad(0)];
+        double sx = 0.5 * y0.x, sy = 0.5 * y0.y;
+        const int step = (2 * i + 1) % m4;
+        int m = step;
+        for (int kx = 1; kx < nx; ++kx) {
+          const double2 v = buf1[(size_t)t * ld + fpad(kx)];
+          const double cv = ct[m];
+          sx += v.x * cv; sy += v.y * cv;
+          m += step; if (m >= m4) m -= m4;
+        }
+        zt[((size_t)k * nyh + ky0 + t) * nx + i] = make_double2(sx, sy);    // (the 1/nx of idct is applied in phase C)
+      }
+      __syncthreads();
+      continue;
+    }
     double2* zf = fft_rows(buf0, buf1, a.plan_xe, ld, c.twx, nr, 1.0);
     if (!coupled) {
       double2* zo = (zf == buf0) ? buf1 : buf0;
@@ -618,6 +656,155 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
   cta_partials<1>(c, sn, 18);
 }
 
+// ---- phase D, software-pipelined: every warp stages the inputs of its NEXT (row, 64-point chunk) unit in shared memory
+// with cp.async while it computes the current one, so global-load latency overlaps the fp64 work without holding
+// registers (the plain version above serialises load -> compute -> store per warp).  Needs ny even (16-byte copies).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16_ca(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int ND> struct DStage {   // doubles per staged unit: cc[64] + 2 halos, then 64 each: pk, ro, ao[2 ND], (cxm, cxp)
+  static constexpr int kArr = 2 + 2 * ND + (ND == 2 ? 2 : 0);
+  static constexpr int kDoubles = 64 + 2 + 64 * kArr + 2;     // padded to a multiple of 4 doubles
+  static constexpr int kBytes = kDoubles * 8;
+};
+
+template <int ND, bool HASREF>
+__device__ __noinline__ void phase_D_pipe(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d,
+                                          double* alp_d, const double* rho_ref, const double* alp_ref, double sigma, double epsl) {
+  constexpr int NA = 2 * ND, VW = 2;
+  using ST = DStage<ND>;
+  const CoopArgs& a = c.a;
+  const MarchParams& p = a.p;
+  const int K = p.K, nx = a.nxe, ny = a.nye, egno = p.egno;
+  const size_t n = (size_t)nx * ny, KN = (size_t)K * n;
+  const Recip rc(p.dt, a.dxe, a.dye, sigma);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int ny2 = ny / VW, nchunk = (ny2 + 31) >> 5;
+  const long long units = (long long)K * nx * nchunk, ustride = (long long)gridDim.x * nwarp;
+  double* stage0 = reinterpret_cast<double*>(c.work) + (size_t)warp * 2 * ST::kDoubles;
+  double s_dr = 0.0, s_rr = 0.0, s_or = 0.0, s_nan = 0.0;
+  double s_da[NA], s_aa[NA], s_oa[NA];
+#pragma unroll
+  for (int q = 0; q < NA; ++q) { s_da[q] = 0.0; s_aa[q] = 0.0; s_oa[q] = 0.0; }
+
+  auto decode = [&](long long unit, int& k, int& i, int& ch) {
+    const int r = (units < (1LL << 24)) ? fast_div_exact((int)unit, nchunk, c.inv_nchunk) : (int)(unit / nchunk);
+    ch = (int)(unit - (long long)r * nchunk);
+    k = fast_div_exact(r, nx, c.inv_nx);
+    i = r - k * nx;
+  };
+  auto issue = [&](long long unit, double* st) {
+    int k, i, ch;
+    decode(unit, k, i, ch);
+    const int nvalid = min(32, ny2 - ch * 32);
+    const int j0 = ch * 64;
+    const size_t row = (size_t)i * ny, g0 = (size_t)k * n + row + j0;
+    const double* pb1 = phib + (size_t)(k + 1) * n;
+    if (lane < nvalid) {
+      const int o = 2 * lane;
+      cp_async16_ca(st + o, pb1 + row + j0 + o);
+      double* q = st + 66;
+      cp_async16(q + o, phib + g0 + o); q += 64;
+      cp_async16(q + o, rho_s + g0 + o); q += 64;
+#pragma unroll
+      for (int t = 0; t < NA; ++t) { cp_async16(q + o, alp_s + (size_t)t * KN + g0 + o); q += 64; }
+      if (ND == 2) {
+        const Nbr bx = nbr(i, nx, p.bc_x);
+        cp_async16_ca(q + o, pb1 + (size_t)bx.m * ny + j0 + o); q += 64;
+        cp_async16_ca(q + o, pb1 + (size_t)bx.p * ny + j0 + o);
+      }
+    }
+    if (lane == 0) cp_async8(st + 64, pb1 + row + ((j0 == 0) ? ny - 1 : j0 - 1));
+    if (lane == 1) { const int je = j0 + 2 * nvalid; cp_async8(st + 65, pb1 + row + ((je == ny) ? 0 : je)); }
+  };
+
+  long long unit = (long long)blockIdx.x * nwarp + warp;
+  int sidx = 0;
+  if (unit < units) issue(unit, stage0);
+  cp_async_commit();
+  for (; unit < units; unit += ustride) {
+    const long long un = unit + ustride;
+    double* st = stage0 + (size_t)sidx * ST::kDoubles;
+    if (un < units) issue(un, stage0 + (size_t)(sidx ^ 1) * ST::kDoubles);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    int k, i, ch;
+    decode(unit, k, i, ch);
+    const int nvalid = min(32, ny2 - ch * 32);
+    if (lane < nvalid) {
+      const int j = ch * 64 + 2 * lane, o = 2 * lane;
+      const size_t g = (size_t)k * n + (size_t)i * ny + j;
+      const double2 cc = *reinterpret_cast<const double2*>(st + o);
+      const double c_l = (lane == 0) ? st[64] : st[o - 1];
+      const double c_r = (lane == nvalid - 1) ? st[65] : st[o + 2];
+      const double* q = st + 66;
+      const double2 pk = *reinterpret_cast<const double2*>(q + o); q += 64;
+      const double2 ro = *reinterpret_cast<const double2*>(q + o); q += 64;
+      double2 ao[NA];
+#pragma unroll
+      for (int t = 0; t < NA; ++t) { ao[t] = *reinterpret_cast<const double2*>(q + o); q += 64; }
+      double2 cxm = make_double2(0.0, 0.0), cxp = cxm;
+      const Nbr bx = nbr(i, nx, p.bc_x);
+      if (ND == 2) { cxm = *reinterpret_cast<const double2*>(q + o); q += 64; cxp = *reinterpret_cast<const double2*>(q + o); }
+      Vec<VW> rref, aref[NA];
+      if (HASREF) {
+        rref = ldv<VW>(rho_ref + g);
+#pragma unroll
+        for (int t = 0; t < NA; ++t) aref[t] = ldv<VW>(alp_ref + (size_t)t * KN + g);
+      }
+      const double cx = (ND == 2 || egno == 3) ? c.cx[i] : 0.0;
+      Vec<VW> rn, an[NA];
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        const double c0 = e ? cc.y : cc.x;
+        const double cym = e ? cc.x : c_l, cyp = e ? c_r : cc.y;
+        double aoe[NA], ane[NA], rne;
+#pragma unroll
+        for (int t = 0; t < NA; ++t) aoe[t] = e ? ao[t].y : ao[t].x;
+        const double roe = e ? ro.y : ro.x;
+        dual_point<ND>(egno, c0, e ? cxm.y : cxm.x, e ? cxp.y : cxp.x, cym, cyp, e ? pk.y : pk.x, roe, aoe, cx, c.cy[j + e], bx.wm,
+                       bx.wp, sigma, epsl, rc, rne, ane);
+        rn.e[e] = rne;
+        double d = rne - roe;
+        s_dr += d * d; s_rr += rne * rne; s_nan += is_nan(rne) ? 1.0 : 0.0;
+        if (HASREF) { d = rne - rref.e[e]; s_or += d * d; }
+#pragma unroll
+        for (int t = 0; t < NA; ++t) {
+          an[t].e[e] = ane[t];
+          d = ane[t] - aoe[t];
+          s_da[t] += d * d; s_aa[t] += ane[t] * ane[t];
+          if (HASREF) { d = ane[t] - aref[t].e[e]; s_oa[t] += d * d; }
+        }
+      }
+      stv<VW>(rho_d + g, rn);
+#pragma unroll
+      for (int t = 0; t < NA; ++t) stv<VW>(alp_d + (size_t)t * KN + g, an[t]);
+    }
+    __syncwarp();     // every lane is done with this stage before it is refilled in the next round
+    sidx ^= 1;
+  }
+  cp_async_wait<0>();
+  double sums[15];
+#pragma unroll
+  for (int q = 0; q < 15; ++q) sums[q] = 0.0;
+  sums[0] = s_dr; sums[1] = s_rr; sums[10] = s_or;
+#pragma unroll
+  for (int q = 0; q < NA; ++q) { sums[2 + 2 * q] = s_da[q]; sums[3 + 2 * q] = s_aa[q]; sums[11 + q] = s_oa[q]; }
+  cta_partials<15>(c, sums, 0);
+  const double sn[1] = {s_nan};
+  cta_partials<1>(c, sn, 18);
+}
+
 // runtime -> compile-time dispatch of the templated phases
 __device__ __forceinline__ void run_A(Ctx& c, int cd, double epsl) {
   const bool v2 = (c.a.nye & 1) == 0;
@@ -630,6 +817,13 @@ __device__ __forceinline__ void run_C(Ctx& c, const double* pp, double* pn, doub
 __device__ __forceinline__ void run_D(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d, double* alp_d,
                                       const double* rho_ref, const double* alp_ref, double sigma, double epsl) {
   const bool v2 = (c.a.nye & 1) == 0;
+  if (c.a.d_pipe) {
+    if (rho_ref) { if (c.a.has_x) phase_D_pipe<2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
+                   else phase_D_pipe<1, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl); }
+    else { if (c.a.has_x) phase_D_pipe<2, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
+           else phase_D_pipe<1, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
+    return;
+  }
   if (rho_ref) {
     if (c.a.has_x) { if (v2) phase_D<2, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
                      else phase_D<2, 1, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl); }
@@ -913,7 +1107,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
 // ------------------------------------------- host side -------------------------------------------
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-struct CoopGeom { int nxe, nye, nyh, TR, TKY, grid; size_t smem; };
+struct CoopGeom { int nxe, nye, nyh, TR, TKY, grid, d_pipe; size_t smem; };
 
 static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   CoopGeom g;
@@ -932,7 +1126,12 @@ static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   g.TKY = TKY;
   const size_t smA = (size_t)TR * fft_ld(g.nye) * 16;                 // 2 buffers * TR/2 rows
   const size_t smB = (g.nxe > 1) ? (size_t)2 * TKY * fft_ld(g.nxe) * 16 : 0;
-  g.smem = tab + (smA > smB ? smA : smB);
+  size_t work = smA > smB ? smA : smB;
+  // staging buffers of the pipelined dual sweep: 2 stages per warp
+  const size_t smD = (size_t)kWarps * 2 * ((p.ndim == 2) ? DStage<2>::kBytes : DStage<1>::kBytes);
+  g.d_pipe = ((g.nye & 1) == 0 && smD <= cap && getenv("PDHG_DPIPE") != nullptr) ? 1 : 0;   // opt-in: measured slower (L1 shrinks)
+  if (g.d_pipe && smD > work) work = smD;
+  g.smem = tab + work;
   g.grid = sm_count * kCtasPerSm;
   return g;
 }
@@ -980,7 +1179,7 @@ static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, 
   a.p = p;
   a.w = carve(p, ws);
   a.b = b; a.mode = mode; a.A = 2 * p.ndim;
-  a.nxe = g.nxe; a.nye = g.nye; a.nyh = g.nyh; a.TR = g.TR; a.TKY = g.TKY;
+  a.nxe = g.nxe; a.nye = g.nye; a.nyh = g.nyh; a.TR = g.TR; a.TKY = g.TKY; a.d_pipe = g.d_pipe;
   a.has_x = (p.ndim == 2);
   if (p.ndim == 1) {
     a.dxe = 1.0; a.dye = p.dx; a.coef_xe = p.coef_x; a.coef_ye = p.coef_x; a.tw_xe = p.tw_x; a.tw_ye = p.tw_x;

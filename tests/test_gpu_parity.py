@@ -29,7 +29,7 @@ def _problem(pk, d):
   return egno, ndim, nx, ny, n_ctrl, bc, x_arr, fns
 
 
-OPS = [n for n in golden_names("op_") if "eg3" not in n]
+OPS = golden_names("op_")
 
 
 @pytest.mark.parametrize("name", OPS)
@@ -45,14 +45,15 @@ def test_update_operators_vs_reference_golden(pk, name):
   assert relmax(pn, d["phi_next"]) < TOL
   r1, a1, e1 = upd.update_dual_oneiter(d["phi_bar"], d["rho"], 70.0, alp, float(d["sigma"]), dt, dsp, epsl, x_arr, None, bc, fns, ndim)
   assert relmax(r1, d["rho_sweep1"]) < TOL and relmax(np.stack(a1), d["alp_sweep1"]) < TOL
-  assert abs(e1 - float(d["err_sweep1"])) <= 1e-9 * abs(float(d["err_sweep1"]))
+  eref = float(d["err_sweep1"])       # NaN for egno 3 (0/0 on the untouched y pair, update_fns_in_pdhg.py:164)
+  assert (np.isnan(e1) and np.isnan(eref)) or abs(e1 - eref) <= 1e-9 * abs(eref)
   rN, aN, _, n_inner = upd._update_dual(d["phi_bar"], d["rho"], 70.0, alp, float(d["sigma"]), dt, dsp, epsl, fns, x_arr, None, ndim, bc,
                                         10, float(d["eps"]))
   assert relmax(rN, d["rho_dual"]) < TOL and relmax(np.stack(aN), d["alp_dual"]) < TOL
   assert n_inner == int(d["n_inner"])
 
 
-SOLVES = [n for n in golden_names("solve_") if "eg3" not in n]
+SOLVES = golden_names("solve_")
 
 
 @pytest.mark.parametrize("path", [1, 2])
