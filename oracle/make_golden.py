@@ -159,6 +159,7 @@ SOLVE_CASES = [
   ("solve_2d_eg1_10x8_nt5_tsp3",    1, 2, 10, 8, 5, 3, 0.05, 0.05, 600, 200, (1.0, 1.0, 1.0)),
   ("solve_2d_eg2_8x8_nt3",          2, 2, 8, 8, 3, 2, 0.0, 0.1, 800, 300, (1.0, 1.0, 1.0)),
   ("solve_2d_eg3_10x12_nt3",        3, 2, 10, 12, 3, 2, 0.1, 0.05, 500, 100, (1.0, 1.0, 1.0)),
+  ("solve_1d_eg1_nx32_nt5_failed",  1, 1, 32, 1, 5, 2, 5.0, 0.1, 400, 10000, (1.0, 1.0, 1.0)),   # every step size NaNs: "algorithm failed"
 ]
 
 
@@ -176,9 +177,17 @@ def run_solve_case(name, egno, ndim, nx, ny, nt, tsp, epsl, stepsz, nmax, pf, pr
     ((res_ref, errs_ref), log) = quiet(
       ref_sol.PDHG_multi_step, prim_ref, dual_ref, fns_ref, g_ref, x_arr, ndim, nt, nspatial, dt, dspatial, 70.0,
       time_step_per_PDHG=tsp, epsl=epsl, stepsz_param=stepsz, n_ctrl=n_ctrl, fv=fv_ref, N_maxiter=nmax, print_freq=pf, eps=1e-6)
-  except ValueError:
-    # reference crashes on concatenate([]) when block 0 fails (utils_pdhg_solver.py:215)
+  except (ValueError, UnboundLocalError):
+    # reference crashes (UnboundLocalError on `pdhg_iters` at :206, else concatenate([]) when block 0 fails (utils_pdhg_solver.py:215); its log up to the crash is lost with
+    # the redirected stdout, so the fallback announcements are re-captured line by line below
     failed, res_ref, errs_ref, log = True, None, [], ""
+    buf = io.StringIO()
+    try:
+      with contextlib.redirect_stdout(buf), np.errstate(all='ignore'):
+        ref_sol.PDHG_multi_step(prim_ref, dual_ref, fns_ref, g_ref, x_arr, ndim, nt, nspatial, dt, dspatial, 70.0, time_step_per_PDHG=tsp,
+                                epsl=epsl, stepsz_param=stepsz, n_ctrl=n_ctrl, fv=fv_ref, N_maxiter=nmax, print_freq=pf, eps=1e-6)
+    except (ValueError, UnboundLocalError):
+      log = buf.getvalue()
   t_ref = time.time() - t0
   info = {}
   res_orc, errs_orc = orc.solve_HJ(ndim, n_ctrl, egno, epsl, fns_orc, nx, ny, nt, 2.0, 2.0, 1.0, x_arr, 70.0, tsp, stepsz, nmax, pf,
@@ -217,6 +226,11 @@ def run_solve_case(name, egno, ndim, nx, ny, nt, tsp, epsl, stepsz, nmax, pf, pr
 def main():
   os.makedirs(GOLD, exist_ok=True)
   ok = True
+  only = sys.argv[1] if len(sys.argv) > 1 else None     # optional substring filter: regenerate selected cases only
+  global OP_CASES, SOLVE_CASES
+  if only:
+    OP_CASES = [c for c in OP_CASES if only in c[0]]
+    SOLVE_CASES = [c for c in SOLVE_CASES if only in c[0]]
   for seed, case in enumerate(OP_CASES):
     w = run_op_case(*case, seed=100 + seed)
     print("%-32s oracle-vs-reference rel-Linf %.2e" % (case[0], w), flush=True)

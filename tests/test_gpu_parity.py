@@ -53,7 +53,7 @@ def test_update_operators_vs_reference_golden(pk, name):
   assert n_inner == int(d["n_inner"])
 
 
-SOLVES = golden_names("solve_")
+SOLVES = [n for n in golden_names("solve_") if "failed" not in n]
 
 
 @pytest.mark.parametrize("path", [1, 2])
@@ -82,6 +82,26 @@ def test_solve_HJ_vs_reference_golden(pk, name, path):
   assert relmax(np.concatenate([e.reshape(-1, 2) for e in errs]), d["errs_flat"]) < 1e-7
   for s in d["stepsz_decrements"].tolist():                           # the reference's fallback announcements
     assert "decrease step size to {}".format(s) in log
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_algorithm_failed_path_vs_reference_golden(pk, path):
+  """Every step size 0.1 -> 0.01 NaNs in block 0: the reference announces nine decrements, then 'algorithm failed'
+  (utils_pdhg_solver.py:180-187) and crashes; here the same sequence is reported and the failure is a status."""
+  d = golden("solve_1d_eg1_nx32_nt5_failed")
+  egno, ndim, nx, ny, n_ctrl, bc, x_arr, fns = _problem(pk, d)
+  os.environ["PDHG_FORCE_PATH"] = str(path)
+  try:
+    info = {}
+    (res, errs), log = quiet(pk["rx"].solve_HJ, ndim, n_ctrl, egno, float(d["epsl"]), fns, nx, ny, int(d["nt"]), 2.0, 2.0, 1.0, x_arr, 70.0,
+                             int(d["tsp"]), float(d["stepsz"]), int(d["N_maxiter"]), int(d["print_freq"]), 1e-6, bc, info=info)
+  finally:
+    os.environ.pop("PDHG_FORCE_PATH", None)
+  assert info["sol_nan"] and info["blocks_done"] == 0 and res[0][1] is None and errs == []
+  assert info["stepsz_final"] == d["stepsz_decrements"].tolist()[-1]
+  for s in d["stepsz_decrements"].tolist():
+    assert "decrease step size to {}".format(s) in log
+  assert "algorithm failed" in log
 
 
 def test_cfg1_readme_example_full_solve(pk):
