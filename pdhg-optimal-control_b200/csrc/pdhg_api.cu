@@ -13,6 +13,8 @@
 namespace pdhg {
 // kernels / launchers implemented in the other translation units
 cudaError_t launch_pdhg1d_cta(const MarchParams& p, int B, cudaStream_t stream);
+cudaError_t launch_pdhg1d_k1(const MarchParams& p, int B, cudaStream_t stream);
+bool pdhg1d_k1_supported(int nx, int K, int green_R);
 size_t pdhg1d_cta_smem_bytes(int nx, int K);
 cudaError_t launch_pdhg_coop(const MarchParams& p, int B, void* ws, cudaStream_t stream, long long* launches);
 size_t pdhg_coop_workspace_bytes(const MarchParams& p, int B);
@@ -48,7 +50,8 @@ struct pdhg_handle {
   int B = 1;
   long long launches = 0;
   std::vector<void*> owned;
-  double *coef_x = nullptr, *coef_y = nullptr, *diag = nullptr, *dct_cos = nullptr;
+  double *coef_x = nullptr, *coef_y = nullptr, *diag = nullptr, *dct_cos = nullptr, *green = nullptr;
+  int green_R = -1;
   double2 *tw_x = nullptr, *tw_y = nullptr;
   FftPlan plan_x{}, plan_y{}, plan_1d{};
   double *epsl = nullptr, *stepsz = nullptr, *delta = nullptr, *floor_ = nullptr;
@@ -222,6 +225,29 @@ extern "C" int pdhg_create(const pdhg_config* cfg, const double* coef_x, const d
   }
   CB(dalloc(h, &h->diag, diag.size()));
   CB(cudaMemcpy(h->diag, diag.data(), diag.size() * sizeof(double), cudaMemcpyHostToDevice));
+  if (c.ndim == 1 && c.K == 1 && c.nx <= 2048) {
+    // G = IFFT(1/d), d = (lambda + C)^pow + Ct/dt^2: the K = 1 preconditioner as a circular convolution (pdhg1d_k1.cu).
+    // Real and even; evaluated in long double; R = last tap with |G[j]| >= 2^-56 G[0].
+    const int n = c.nx, half = n / 2;
+    std::vector<long double> cs(n), inv(n);
+    for (int m = 0; m < n; ++m) cs[m] = cosl(2.0L * 3.14159265358979323846264338327950288L * m / (long double)n);
+    const long double ct2 = (long double)c.Ct / ((long double)c.dt * c.dt);
+    for (int k = 0; k < n; ++k) inv[k] = 1.0L / ((long double)diag[k] + ct2);
+    std::vector<double> G(half + 1);
+    for (int j = 0; j <= half; ++j) {
+      long double acc = 0.0L;
+      for (int k = 0; k < n; ++k) acc += inv[k] * cs[(int)(((long long)k * j) % n)];
+      G[j] = (double)(acc / n);
+    }
+    int R = 0;
+    const double thr = ldexp(fabs(G[0]), -56);
+    for (int j = 0; j <= half; ++j) if (fabs(G[j]) >= thr) R = j;
+    if (pdhg1d_k1_supported(n, c.K, R)) {
+      h->green_R = R;
+      CB(dalloc(h, &h->green, (size_t)R + 1));
+      CB(cudaMemcpy(h->green, G.data(), ((size_t)R + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    }
+  }
   CB(dalloc(h, &h->coef_x, (size_t)c.nx));
   CB(cudaMemcpy(h->coef_x, coef_x, c.nx * sizeof(double), cudaMemcpyHostToDevice));
   CB(dalloc(h, &h->coef_y, (size_t)c.ny));
@@ -277,7 +303,8 @@ static void fill_params(pdhg_handle* h, MarchParams* p) {
   p->eps = c.eps; p->rho_alp_iters = c.rho_alp_iters;
   p->max_rec = c.max_rec;
   p->epsl = h->epsl; p->stepsz = h->stepsz; p->stepsz_delta = h->delta; p->stepsz_floor = h->floor_;
-  p->coef_x = h->coef_x; p->coef_y = h->coef_y; p->diag = h->diag; p->dct_cos = h->dct_cos; p->tw_x = h->tw_x; p->tw_y = h->tw_y;
+  p->coef_x = h->coef_x; p->coef_y = h->coef_y; p->diag = h->diag; p->dct_cos = h->dct_cos;
+  p->green = h->green; p->green_R = h->green_R; p->tw_x = h->tw_x; p->tw_y = h->tw_y;
   p->Ct_over_dt2 = (c.ndim == 1 ? c.Ct : 1.0) / (c.dt * c.dt);
   p->plan_x = h->plan_x; p->plan_y = h->plan_y; p->plan_1d = h->plan_1d;
   p->st_phi = h->st_phi; p->st_rho = h->st_rho; p->st_alp = h->st_alp;
@@ -325,7 +352,8 @@ static int run_march(pdhg_handle* h, const MarchParams& p, cudaStream_t s) {
   CU(cudaEventRecord(h->ev0, s));
   struct Rec { pdhg_handle* h; cudaStream_t s; ~Rec() { h->ev_valid = (cudaEventRecord(h->ev1, s) == cudaSuccess); } } rec{h, s};
   if (h->path == 1) {
-    CU(launch_pdhg1d_cta(p, h->B, s));
+    if (h->green_R >= 0 && getenv("PDHG_NO_K1") == nullptr) CU(launch_pdhg1d_k1(p, h->B, s));   // K = 1 register-resident kernel
+    else CU(launch_pdhg1d_cta(p, h->B, s));
     h->launches += 1;
   } else {
     CU(launch_pdhg_coop(p, h->B, h->ws, s, &h->launches));

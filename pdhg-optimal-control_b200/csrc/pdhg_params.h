@@ -41,6 +41,8 @@ struct MarchParams {
   const double* coef_x;            // [nx]  a(x) (egno 1,2) / x (egno 3)
   const double* coef_y;            // [ny]
   const double* diag;              // [nx*nyh] per-mode (lambda+C)^pow (1-D) or lambda+C (2-D)
+  const double* green;             // [green_R + 1] taps of G = IFFT(1/d) for the K = 1 single-CTA kernel (1-D), else null
+  int green_R;                     // -1: not available
   const double* dct_cos;           // [4 nx] cos(pi m/(2 nx)) for the Neumann-x DCT-II (bc_x = 1), else null
   const double2* tw_x;             // [nx] master twiddles exp(-2 pi i m/nx)
   const double2* tw_y;             // [ny]
