@@ -805,6 +805,34 @@ __device__ __noinline__ void phase_D_pipe(Ctx& c, const double* phib, const doub
   cta_partials<1>(c, sn, 18);
 }
 
+// ---- phase E (only after an inner loop of more than one sweep): outer-iteration differences of the dual variables,
+// sum (x_next - x_prev)^2, for err2 (utils_pdhg_solver.py:61-68).  Reading the previous iterate once here instead of
+// in every extra sweep keeps the extra sweeps at the traffic of the first one.  CTA partials: slot 10 rho, 11+q alp q.
+template <int VW>
+__device__ __noinline__ void phase_E(Ctx& c, const double* rho_n, const double* alp_n, const double* rho_o, const double* alp_o) {
+  const CoopArgs& a = c.a;
+  const size_t KN = (size_t)a.p.K * a.nxe * a.nye;
+  const int A = a.A;
+  const size_t stride = (size_t)gridDim.x * blockDim.x * VW;
+  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VW; g < KN; g += stride) {
+    {
+      const Vec<VW> x = ldv<VW>(rho_n + g), y = ldv<VW>(rho_o + g);
+#pragma unroll
+      for (int e = 0; e < VW; ++e) { const double d = x.e[e] - y.e[e]; s[0] += d * d; }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q < A) {
+        const Vec<VW> x = ldv<VW>(alp_n + (size_t)q * KN + g), y = ldv<VW>(alp_o + (size_t)q * KN + g);
+#pragma unroll
+        for (int e = 0; e < VW; ++e) { const double d = x.e[e] - y.e[e]; s[1 + q] += d * d; }
+      }
+    }
+  }
+  cta_partials<5>(c, s, 10);
+}
+
 // runtime -> compile-time dispatch of the templated phases
 __device__ __forceinline__ void run_A(Ctx& c, int cd, double epsl) {
   const bool v2 = (c.a.nye & 1) == 0;
@@ -995,7 +1023,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
         int j = 0;
         for (; j < p.rho_alp_iters; ++j) {
           if (j == 0) run_D(c, w.phib, w.rho[cd], w.alp[cd], w.rho[nd], w.alp[nd], nullptr, nullptr, sigma, epsl);
-          else run_D(c, w.phib, w.rho[nd], w.alp[nd], w.rho[nd], w.alp[nd], w.rho[cd], w.alp[cd], sigma, epsl);
+          else run_D(c, w.phib, w.rho[nd], w.alp[nd], w.rho[nd], w.alp[nd], nullptr, nullptr, sigma, epsl);   // in place
           grid_gather(c, v);
           if (j == 0) { e1s0 = v[15]; e1s1 = v[16]; e1nan = v[17]; }
           double err = v[0] / v[1];
@@ -1004,14 +1032,23 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
           if (err < p.eps) { ++j; break; }
         }
         inner_total += j;
-        TICK(3);
         const bool multi = (j > 1);
+        double vo[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (multi) {
+          if ((a.nye & 1) == 0) phase_E<2>(c, w.rho[nd], w.alp[nd], w.rho[cd], w.alp[cd]);
+          else phase_E<1>(c, w.rho[nd], w.alp[nd], w.rho[cd], w.alp[cd]);
+          double v2[kNQ];
+          grid_gather(c, v2);
+#pragma unroll
+          for (int q = 0; q < 5; ++q) vo[q] = v2[10 + q];
+        }
+        TICK(3);
         err1 = sqrt(e1s0) / sqrt(S_row0 + e1s1);
-        err2 = sqrt(multi ? v[10] : v[0]) / sqrt(S_rho);
+        err2 = sqrt(multi ? vo[0] : v[0]) / sqrt(S_rho);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if (q < A) {
-            const double na = sqrt(S_alp[q]), ne = sqrt(multi ? v[11 + q] : v[2 + 2 * q]);
+            const double na = sqrt(S_alp[q]), ne = sqrt(multi ? vo[1 + q] : v[2 + 2 * q]);
             if (na < 1e-6 && ne > 1e-6) err2 += ne; else if (na >= 1e-6) err2 += ne / na;
           }
         }
