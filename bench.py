@@ -209,9 +209,9 @@ def oracle_iterations(pb, n_iters):
 def cpu_baseline(pb, budget_s=20.0):
   t1, it1 = oracle_iterations(pb, 1)
   n = int(max(1, min(200, budget_s / max(t1, 1e-6))))
-  t, it = oracle_iterations(pb, n)
+  t, it = (t1, it1) if n == 1 else oracle_iterations(pb, n)
   return {"value": it * pb["N"] / t, "unit": "grid-point updates/s", "cores": 1, "kind": "port",
-          "iters_per_s": it / t, "sample": "%d outer PDHG iterations of block 0 of the same workload, NumPy fp64 oracle, 1 process "
+          "iters_per_s": it / t, "sample": "the first %d outer PDHG iteration(s) of block 0 of the same workload from the cold initial state, NumPy fp64 oracle, 1 process "
           "(JAX is not installable here, so the reference's own JAX-CPU path cannot be timed)" % it}
 
 
@@ -241,6 +241,25 @@ def batched_sample(device):
   return {"workload": "BASELINE configs[3] sample: %d of 4096 instances, nx=1024, first %d of 256 blocks, host buffers in/out" % (B, nblk),
           "instances": B, "total_iters": its, "seconds": t, "pdhg_iters_per_s": its / t, "grid_point_updates_per_s": its * nx / t,
           "all_converged": bool((logs.status == 0).all())}
+
+
+def time_to_tol(name, device, nblocks=None):
+  """Wall time of the reference-facing solve_HJ call (host arrays in/out) to the reference's own stopping rule."""
+  from pdhg_b200 import run_example as rx
+  pb = make_problem(name)
+  nt = pb["nt"] if nblocks is None else nblocks * pb["K"] + 1
+  T = 1.0 if nblocks is None else pb["dt"] * (nt - 1)
+  info = {}
+  run = lambda: rx.solve_HJ(pb["ndim"], pb["n_ctrl"], pb["egno"], pb["epsl"], pb["fns"], pb["nx"], pb["ny"], nt, 2.0, 2.0, T, pb["x_arr"], 70.0,
+                            pb["tsp"], 0.1, 1000000, 10000, 1e-6, pb["bc"], info=info)
+  with contextlib.redirect_stdout(io.StringIO()):
+    t0 = time.perf_counter()
+    run()
+    t = time.perf_counter() - t0
+  its = int(sum(info["block_iters"]))
+  return {"workload": DESCR[name].split(" (")[0] + (" — all %d time blocks" % (nt - 1) if nblocks is None else " — first %d time blocks" % nblocks)
+                      + ", solve_HJ with stepsz_param=0.1 incl. the NaN fallback", "seconds_to_tol": t, "total_iters": its,
+          "blocks": len(info["block_iters"]), "stepsz_used": sorted(set(info["stepsz_used"]), reverse=True), "pdhg_iters_per_s": its / t}
 
 
 def secondary(name, device, iters):
@@ -380,6 +399,11 @@ def main():
             others[nm] = secondary(nm, local, its)
           except Exception as ex:   # secondary lines never break the headline
             others[nm] = {"error": repr(ex)}
+      for nm, nb in (("cfg1", None), ("cfg3_tsp2", 3)):
+        try:
+          others["time_to_tol_" + nm] = time_to_tol(nm, local, nb)
+        except Exception as ex:
+          others["time_to_tol_" + nm] = {"error": repr(ex)}
       try:
         others["cfg4_sample"] = batched_sample(local)
       except Exception as ex:

@@ -267,3 +267,56 @@ def test_device_tensors_stay_on_device(pk):
                             dspatial_of(d), fns, None, float(d["epsl"]), x24, None, 0)
   assert isinstance(pn, torch.Tensor) and pn.is_cuda
   assert relmax(pn.cpu().numpy(), d["phi_next"]) < TOL
+
+
+def test_batched_2d_instances_cooperative_path(pk):
+  """B = 3 independent 2-D instances (different epsl) through one handle of the cooperative kernel == separate solves."""
+  rx = pk["rx"]
+  nx, ny, nt = 16, 12, 3
+  n_ctrl, bc, _ = rx.problem_setup(1, 2)
+  x_arr = rx.make_x_arr(2, nx, ny, 2.0, 2.0)
+  fns, _ = quiet(pk["sf"].set_up_example_fns, 1, 2, 0)
+  g1 = pk["sf"].set_up_J(1, 2, (2.0, 2.0))(x_arr)
+  g = np.concatenate([g1, 0.5 * g1, 1.5 * g1], axis=0)
+  epsl = np.array([0.0, 0.05, 0.1])
+  phi, rho, alp, logs = rx.solve_HJ_batch(2, n_ctrl, 1, epsl, fns, nx, ny, nt, 2.0, 2.0, 0.2, x_arr, g, 70.0, 2, 0.1, 400, 100, 1e-6, bc)
+  assert phi.shape == (3, nt, nx, ny) and alp.shape == (3, 4, nt - 1, nx, ny, 2)
+  for b in range(3):
+    p1, r1, a1, l1 = rx.solve_HJ_batch(2, n_ctrl, 1, epsl[b:b + 1], fns, nx, ny, nt, 2.0, 2.0, 0.2, x_arr, g[b:b + 1], 70.0, 2, 0.1, 400, 100,
+                                       1e-6, bc)
+    assert np.array_equal(p1[0], phi[b]) and np.array_equal(a1[0], alp[b]) and np.array_equal(l1.iters[0], logs.iters[b])
+  assert (alp[..., 1][:, :2] == 0).all() and (alp[..., 0][:, 2:] == 0).all()     # structurally-zero control components
+
+
+def test_multi_step_with_device_tensors_and_save_middle(pk, tmp_path):
+  import torch
+  from pdhg_b200.solver import load_middle_solution
+  rx, upd, sol = pk["rx"], pk["upd"], pk["sol"]
+  d = golden("solve_1d_eg1_nx40_nt11")
+  egno, ndim, nx, ny, n_ctrl, bc, x_arr, fns = _problem(pk, d)
+  nt = int(d["nt"])
+  g = torch.from_numpy(pk["sf"].set_up_J(1, 1, (2.0,))(x_arr)).cuda()
+  (res, errs), _ = quiet(sol.PDHG_multi_step, upd.NativeUpdatePrimal(1, bc), upd.NativeUpdateDual(bc), fns, g, x_arr, 1, nt, (nx,), 1.0 / (nt - 1),
+                         (2.0 / nx,), 70.0, time_step_per_PDHG=2, epsl=0.0, stepsz_param=0.1, n_ctrl=1, N_maxiter=1000000, print_freq=1000,
+                         eps=1e-6, save_middle_dir=str(tmp_path), save_middle_prefix="mid")
+  mi, phi, rho, alp = res[0]
+  assert isinstance(phi, torch.Tensor) and phi.is_cuda
+  assert relmax(phi.cpu().numpy(), d["phi"]) < TOL and relmax(alp.cpu().numpy(), d["alp"]) < TOL
+  mid = load_middle_solution(str(tmp_path), "mid")       # [max_iters, phi_all, rho_all, alp_all, errs_all] (utils_pdhg_solver.py:211-212)
+  assert mid[0] == int(d["max_iters"]) and len(mid[1]) == nt - 1 and len(mid[4]) == nt - 1
+
+
+def test_run_example_cli_saves_reference_pickle_layout(pk, tmp_path):
+  """python -m pdhg_b200.run_example with the reference's flags; the pickle holds (results, errs_all) (solver.py:13-26)."""
+  import pickle, subprocess, sys, glob
+  pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pdhg-optimal-control_b200")
+  env = dict(os.environ, PYTHONPATH=pkg)
+  r = subprocess.run([sys.executable, "-m", "pdhg_b200.run_example", "--ndim", "1", "--epsl", "0", "--egno", "1", "--nx", "40", "--nt", "11",
+                      "--stepsz_param", "0.1", "--print_freq", "1000"], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+  assert r.returncode == 0, r.stderr[-2000:]
+  assert "pdhg conv. Max err is" in r.stdout and "PDHG converges at iter 4615" in r.stdout
+  files = glob.glob(str(tmp_path / "check_points" / "*" / "eg1_1d" / "nt11_nx40.pickle"))
+  assert len(files) == 1
+  results, errs_all = pickle.load(open(files[0], "rb"))
+  d = golden("solve_1d_eg1_nx40_nt11")
+  assert results[0][0] == int(d["max_iters"]) and relmax(results[0][1], d["phi"]) < TOL and len(errs_all) == 10
