@@ -104,6 +104,10 @@ double pdhg_last_kernel_ms(const pdhg_handle* h);
  * B FFT_x+t-solve, C IFFT_y+phi update, D dual sweeps+reduction, -, setup/records/output}, out16[6..15] = sub-steps seen
  * by CTA 0 (A: compute, fft, store; B: pass 1, 2, 3; C: load, fft, update; spare); zeros on the single-CTA path */
 int pdhg_phase_times(pdhg_handle* h, double* out16);
+/* diagnostic (profiling aid): launches ONE phase of the cooperative kernel `reps` times on the workspace left by the last
+ * march, so that ncu sees each phase as its own launch: phase 0 = A, 1 = B (pass_mask bit 0/1/2 = x-FFT / t-solve / inverse
+ * x-FFT), 2 = C, 3 = D + reduction; `step` = tau or sigma.  Results are meaningless; caller buffers are not touched. */
+int pdhg_debug_phase(pdhg_handle* h, int phase, int pass_mask, double step, int reps);
 /* number of kernel launches issued through this handle so far */
 int64_t pdhg_launch_count(const pdhg_handle* h);
 

@@ -19,6 +19,7 @@ size_t pdhg1d_cta_smem_bytes(int nx, int K);
 cudaError_t launch_pdhg_coop(const MarchParams& p, int B, void* ws, cudaStream_t stream, long long* launches);
 size_t pdhg_coop_workspace_bytes(const MarchParams& p, int B);
 cudaError_t coop_phase_times(const MarchParams& p, void* ws, double* out6);
+cudaError_t launch_debug_phase(const MarchParams& p, void* ws, int phase, int pass_mask, double step, cudaStream_t stream);
 cudaError_t launch_pack_alp(const double* ref_layout, double* planar, int B, int A, size_t kn, int n_ctrl, int ndim,
                             int egno, int to_planar, cudaStream_t stream);
 cudaError_t launch_init_state(const MarchParams& p, const double* g, int B, cudaStream_t stream);
@@ -160,6 +161,16 @@ extern "C" int pdhg_phase_times(pdhg_handle* h, double* out6 /* 16 doubles */) {
   fill_params(h, &p);
   CU(cudaSetDevice(h->cfg.device));
   CU(coop_phase_times(p, h->ws, out6));
+  return PDHG_OK;
+}
+
+extern "C" int pdhg_debug_phase(pdhg_handle* h, int phase, int pass_mask, double step, int reps) {
+  if (!h || phase < 0 || phase > 3 || reps < 1) return fail(PDHG_ERR_ARG, "pdhg_debug_phase: bad argument");
+  CU(cudaSetDevice(h->cfg.device));
+  MarchParams p;
+  fill_params(h, &p);
+  for (int r = 0; r < reps; ++r) { CU(launch_debug_phase(p, h->ws, phase, pass_mask, step, nullptr)); h->launches += 1; }
+  CU(cudaDeviceSynchronize());
   return PDHG_OK;
 }
 

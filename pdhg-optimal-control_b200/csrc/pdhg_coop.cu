@@ -46,7 +46,7 @@ struct CoopWs {
   double* phase_ns;   // [8] accumulated device time per phase of the last march (A, B, C, D+reduce, records, setup/output)
 };
 
-enum : int { MODE_MARCH = 0, MODE_PRIMAL = 1, MODE_DUAL = 2, MODE_TABLES = 3 };
+enum : int { MODE_MARCH = 0, MODE_PRIMAL = 1, MODE_DUAL = 2, MODE_TABLES = 3, MODE_PHASE = 4 };
 
 struct CoopArgs {
   MarchParams p;
@@ -58,6 +58,7 @@ struct CoopArgs {
   int nyh;            // nye/2 + 1
   int TR, TKY;        // rows per y-FFT tile (even), ky rows per x-FFT tile
   int has_x;          // 0 for a 1-D problem
+  int dbg_phase, dbg_pass;   // MODE_PHASE (profiling): phase id 0..3 = A,B,C,D and pass mask of phase B (bit 0,1,2)
   int d_pipe;         // 1: cp.async-pipelined dual sweep (ny even and the staging buffers fit shared memory)
   double dxe, dye;
   const double* coef_xe;
@@ -384,8 +385,9 @@ __device__ __noinline__ void phase_B(Ctx& c) {
   double2* buf1 = buf0 + (size_t)TKY * ld;
   const int ntile = (nyh + TKY - 1) / TKY;
   const int nunits = K * ntile;
+  const int pmask = (a.mode == MODE_PHASE) ? a.dbg_pass : 7;
   // pass 1: x-FFT of every (k, ky) row; uncoupled modes are solved and transformed back in the same pass
-  for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+  for (int u = blockIdx.x; u < ((pmask & 1) ? nunits : 0); u += gridDim.x) {
     const int k = u / ntile, ky0 = (u - k * ntile) * TKY;
     const int nr = min(TKY, nyh - ky0);
     for (int idx = tid; idx < nr * nx; idx += nth) {
@@ -451,12 +453,12 @@ __device__ __noinline__ void phase_B(Ctx& c) {
   c.grid.sync();
   c.tick(3);
   // pass 2: Thomas over k, one thread per real component of a mode (coalesced across modes)
-  for (size_t w = (size_t)blockIdx.x * nth + tid; w < 2 * modes; w += (size_t)gridDim.x * nth)
+  for (size_t w = (size_t)blockIdx.x * nth + tid; w < ((pmask & 2) ? 2 * modes : 0); w += (size_t)gridDim.x * nth)
     thomas_component(reinterpret_cast<double*>(zt), a.w.den, a.w.tu, K, 2 * modes, w, ct2);
   c.grid.sync();
   c.tick(4);
   // pass 3: inverse x-FFT of every row
-  for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+  for (int u = blockIdx.x; u < ((pmask & 4) ? nunits : 0); u += gridDim.x) {
     const int k = u / ntile, ky0 = (u - k * ntile) * TKY;
     const int nr = min(TKY, nyh - ky0);
     for (int idx = tid; idx < nr * nx; idx += nth) {
@@ -924,6 +926,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
   double* galp = p.st_alp + (size_t)b * A * KN;
   const double epsl = p.epsl[b];
 
+  if (a.mode == MODE_PHASE) {
+    // profiling aid: ONE phase on whatever the workspace holds (left there by a previous march), so that ncu sees each
+    // phase as its own launch.  Results are not meaningful; nothing outside the workspace is written.
+    double v[kNQ];
+    switch (a.dbg_phase) {
+      case 0: run_A(c, 0, epsl); break;
+      case 1: phase_B(c); break;
+      case 2: run_C(c, w.phi[0], w.phi[1], w.phib, a.op_step); break;
+      default: run_D(c, w.phib, w.rho[0], w.alp[0], w.rho[1], w.alp[1], nullptr, nullptr, a.op_step, epsl); grid_gather(c, v); break;
+    }
+    return;
+  }
+
   if (a.mode == MODE_PRIMAL) {
     // phi_next = phi_prev + tau * H1_precond(cont_residual(rho, alp))   (update_fns_in_pdhg.py:135-147)
     grid_copy(w.rho[0], grho, KN);
@@ -1203,7 +1218,8 @@ static CoopWs carve(const MarchParams& p, void* ws) {
 }
 
 static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, const double* op_in, double* op_out,
-                               double op_step, double op_eps, int* op_ninner, double* op_err, cudaStream_t stream) {
+                               double op_step, double op_eps, int* op_ninner, double* op_err, cudaStream_t stream,
+                               int dbg_phase = 0, int dbg_pass = 7) {
   int dev = 0, sms = 0, smem_cap = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -1225,6 +1241,7 @@ static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, 
     a.dxe = p.dx; a.dye = p.dy; a.coef_xe = p.coef_x; a.coef_ye = p.coef_y; a.tw_xe = p.tw_x; a.tw_ye = p.tw_y;
     a.plan_xe = p.plan_x; a.plan_ye = p.plan_y;
   }
+  a.dbg_phase = dbg_phase; a.dbg_pass = dbg_pass;
   a.op_phi_in = op_in; a.op_phi_out = op_out; a.op_step = op_step; a.op_eps = op_eps; a.op_ninner = op_ninner; a.op_err = op_err;
   e = cudaFuncSetAttribute(pdhg_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return e;
@@ -1237,6 +1254,10 @@ static cudaError_t ensure_tables(const MarchParams& p, void* ws, cudaStream_t st
   if (p.K == 1 || p.Ct_over_dt2 == 0.0) return cudaSuccess;
   ++*launches;
   return coop_launch(p, ws, 0, MODE_TABLES, nullptr, nullptr, 0.0, 0.0, nullptr, nullptr, stream);
+}
+
+cudaError_t launch_debug_phase(const MarchParams& p, void* ws, int phase, int pass_mask, double step, cudaStream_t stream) {
+  return coop_launch(p, ws, 0, MODE_PHASE, nullptr, nullptr, step, 0.0, nullptr, nullptr, stream, phase, pass_mask);
 }
 
 cudaError_t coop_phase_times(const MarchParams& p, void* ws, double* out6) {

@@ -17,7 +17,7 @@ INST_OK, INST_SOL_NAN, INST_PAUSED, INST_LOG_OVERFLOW = 0, 1, 3, 4
 END_CONVERGED, END_NAN, END_MAXITER, END_PAUSED = 0, 1, 2, 3
 LOG_COLS = 4
 
-EXPORTS = ("pdhg_create", "pdhg_destroy", "pdhg_last_error", "pdhg_path", "pdhg_launch_count", "pdhg_last_kernel_ms", "pdhg_phase_times", "pdhg_update_primal",
+EXPORTS = ("pdhg_create", "pdhg_destroy", "pdhg_last_error", "pdhg_path", "pdhg_launch_count", "pdhg_last_kernel_ms", "pdhg_phase_times", "pdhg_debug_phase", "pdhg_update_primal",
            "pdhg_update_dual", "pdhg_solve_block", "pdhg_multi_step", "pdhg_multi_step_host")
 
 
@@ -66,6 +66,8 @@ def load():
   lib.pdhg_last_kernel_ms.argtypes = [vp]
   lib.pdhg_phase_times.restype = C.c_int
   lib.pdhg_phase_times.argtypes = [vp, dp]
+  lib.pdhg_debug_phase.restype = C.c_int
+  lib.pdhg_debug_phase.argtypes = [vp, C.c_int, C.c_int, dbl, C.c_int]
   lib.pdhg_launch_count.restype = i64
   lib.pdhg_launch_count.argtypes = [vp]
   lib.pdhg_update_primal.restype = C.c_int
@@ -162,6 +164,9 @@ class Solver:
     names = ("A_residual_ffty", "B_fftx_tsolve", "C_iffty_phi", "D_dual_reduce", "unused", "setup_records_output",
              "a_compute", "a_fft", "a_store", "b_pass1", "b_pass2", "b_pass3", "c_load", "c_fft", "c_update", "spare")
     return dict(zip(names, (out / 1e6).tolist()))
+
+  def debug_phase(self, phase, pass_mask=7, step=0.05, reps=1):
+    _check(self.lib.pdhg_debug_phase(self._h, int(phase), int(pass_mask), float(step), int(reps)))
 
   @property
   def launch_count(self):
