@@ -75,18 +75,25 @@ struct CoopArgs {
   double* op_err;
 };
 
+// All shared memory is ONE dynamic region addressed from this symbol, so that every access compiles to LDS/STS (pointers
+// stored in a struct would be generic and compile to LD/ST): [CoopArgs copy][reduction scratch][twx][twy][cx][cy][work].
+extern __shared__ __align__(16) unsigned char g_sm[];
+constexpr int kArgsBytes = (int)((sizeof(CoopArgs) + 15) / 16 * 16);
+constexpr int kRedBytes = kNQ * kWarps * 8;
+__device__ __forceinline__ const CoopArgs& cargs() { return *reinterpret_cast<const CoopArgs*>(g_sm); }
+
 struct Ctx {
-  const CoopArgs& a;
   cg::grid_group grid;
-  const double2* twx;   // smem copies of the twiddle / coefficient tables (L1 is flushed by every grid sync)
-  const double2* twy;
-  const double* cx;
-  const double* cy;
-  double2* work;        // FFT buffers
-  double* red;          // [kNQ*kWarps] static scratch
+  int o_twy, o_cx, o_cy, o_work;     // byte offsets of the tables and of the FFT / staging buffers
   int epoch;
   float inv_nx, inv_nchunk;          // float reciprocals for division-free index math
   unsigned long long tsub[10], tl;   // diagnostic sub-phase timers (CTA 0, thread 0 only)
+  __device__ __forceinline__ double* red() const { return reinterpret_cast<double*>(g_sm + kArgsBytes); }
+  __device__ __forceinline__ const double2* twx() const { return reinterpret_cast<const double2*>(g_sm + kArgsBytes + kRedBytes); }
+  __device__ __forceinline__ const double2* twy() const { return reinterpret_cast<const double2*>(g_sm + o_twy); }
+  __device__ __forceinline__ const double* cx() const { return reinterpret_cast<const double*>(g_sm + o_cx); }
+  __device__ __forceinline__ const double* cy() const { return reinterpret_cast<const double*>(g_sm + o_cy); }
+  __device__ __forceinline__ double2* work() const { return reinterpret_cast<double2*>(g_sm + o_work); }
   __device__ __forceinline__ void tick(int slot) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       unsigned long long t;
@@ -94,7 +101,8 @@ struct Ctx {
       tsub[slot] += t - tl; tl = t;
     }
   }
-  __device__ Ctx(const CoopArgs& a_, double2* sm, double* red_) : a(a_), grid(cg::this_grid()), red(red_), epoch(0) {
+  __device__ Ctx() : grid(cg::this_grid()), epoch(0) {
+    const CoopArgs& a = cargs();
     for (int i = 0; i < 10; ++i) tsub[i] = 0;
     tl = 0;
     inv_nx = 1.0f / (float)a.nxe;
@@ -102,14 +110,17 @@ struct Ctx {
       const int vw = (a.nye & 1) ? 1 : 2;
       inv_nchunk = 1.0f / (float)(((a.nye / vw) + 31) >> 5);
     }
-    double2* tx = sm;
-    double2* ty = tx + a.nxe;
-    double* px = reinterpret_cast<double*>(ty + a.nye);
-    double* py = px + a.nxe;
+    const int o_twx = kArgsBytes + kRedBytes;
+    o_twy = o_twx + 16 * a.nxe;
+    o_cx = o_twy + 16 * a.nye;
+    o_cy = o_cx + 8 * a.nxe;
+    o_work = (o_cy + 8 * a.nye + 15) / 16 * 16;
+    double2* tx = reinterpret_cast<double2*>(g_sm + o_twx);
+    double2* ty = reinterpret_cast<double2*>(g_sm + o_twy);
+    double* px = reinterpret_cast<double*>(g_sm + o_cx);
+    double* py = reinterpret_cast<double*>(g_sm + o_cy);
     for (int i = threadIdx.x; i < a.nxe; i += blockDim.x) { tx[i] = a.tw_xe[i]; px[i] = a.coef_xe[i]; }
     for (int i = threadIdx.x; i < a.nye; i += blockDim.x) { ty[i] = a.tw_ye[i]; py[i] = a.coef_ye[i]; }
-    twx = tx; twy = ty; cx = px; cy = py;
-    work = reinterpret_cast<double2*>(py + a.nye + ((a.nxe + a.nye) & 1));
     __syncthreads();
   }
 };
@@ -124,17 +135,39 @@ __device__ __forceinline__ Nbr nbr(int i, int n, int bc) {
   return r;
 }
 
+// Pointers reach the phase functions through structs, so the compiler would emit GENERIC loads/stores (LD/ST, slower
+// address-space resolution, no read-only path).  Telling it that they are global turns them into LDG/STG.
+template <typename T> __device__ __forceinline__ T* as_global(T* p) { __builtin_assume(__isGlobal(p)); return p; }
+
 // VW-wide (1 or 2 doubles) global access; VW = 2 needs 16-byte alignment (even index on a 256-B aligned array)
 template <int VW> struct Vec { double e[VW]; };
+// Explicit global-space accesses (ld.global / st.global): the workspace pointers arrive through structs, so plain
+// dereferences compile to GENERIC LD/ST (slower address-space resolution); these compile to LDG/STG.
+__device__ __forceinline__ double ldg1(const double* p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(__cvta_generic_to_global(p)));
+  return v;
+}
+__device__ __forceinline__ double2 ldg2(const void* p) {
+  double2 v;
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(__cvta_generic_to_global(p)));
+  return v;
+}
+__device__ __forceinline__ void stg1(double* p, double v) {
+  asm volatile("st.global.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
+__device__ __forceinline__ void stg2(void* p, double2 v) {
+  asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(p)), "d"(v.x), "d"(v.y) : "memory");
+}
 template <int VW> __device__ __forceinline__ Vec<VW> ldv(const double* p) {
   Vec<VW> r;
-  if (VW == 2) { const double2 t = *reinterpret_cast<const double2*>(p); r.e[0] = t.x; r.e[VW - 1] = t.y; }
-  else r.e[0] = *p;
+  if (VW == 2) { const double2 t = ldg2(p); r.e[0] = t.x; r.e[VW - 1] = t.y; }
+  else r.e[0] = ldg1(p);
   return r;
 }
 template <int VW> __device__ __forceinline__ void stv(double* p, const Vec<VW>& v) {
-  if (VW == 2) *reinterpret_cast<double2*>(p) = make_double2(v.e[0], v.e[VW - 1]);
-  else *p = v.e[0];
+  if (VW == 2) stg2(p, make_double2(v.e[0], v.e[VW - 1]));
+  else stg1(p, v.e[0]);
 }
 
 // Reductions.  Every phase block-reduces its per-thread sums and writes ONE row of CTA partials (slot0..slot0+N-1 of
@@ -153,32 +186,32 @@ __device__ __forceinline__ void cta_partials(Ctx& c, const double (&vals)[N], in
   __syncthreads();
   if (lane == 0) {
 #pragma unroll
-    for (int q = 0; q < N; ++q) c.red[q * kWarps + warp] = t[q];
+    for (int q = 0; q < N; ++q) c.red()[q * kWarps + warp] = t[q];
   }
   __syncthreads();
   if (tid < N) {
     double acc = 0.0;
-    for (int w = 0; w < nw; ++w) acc += c.red[tid * kWarps + w];
-    double* part = c.a.w.partials + (size_t)(c.epoch & 1) * gridDim.x * kNQ;
-    part[(size_t)blockIdx.x * kNQ + slot0 + tid] = acc;
+    for (int w = 0; w < nw; ++w) acc += c.red()[tid * kWarps + w];
+    double* part = cargs().w.partials + (size_t)(c.epoch & 1) * gridDim.x * kNQ;
+    part[(size_t)(slot0 + tid) * gridDim.x + blockIdx.x] = acc;      // [quantity][CTA]: the gather reads rows contiguously
   }
 }
 
 __device__ __forceinline__ void grid_gather(Ctx& c, double (&v)[kNQ]) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int G = gridDim.x;
-  const double* part = c.a.w.partials + (size_t)(c.epoch & 1) * G * kNQ;
+  const double* part = cargs().w.partials + (size_t)(c.epoch & 1) * G * kNQ;
   c.grid.sync();
   for (int q = warp; q < kNQ; q += nw) {
     double t = 0.0;
-    for (int g = lane; g < G; g += 32) t += *((const volatile double*)&part[(size_t)g * kNQ + q]);
+    for (int g = lane; g < G; g += 32) t += *((const volatile double*)&part[(size_t)q * G + g]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) c.red[q * kWarps] = t;
+    if (lane == 0) c.red()[q * kWarps] = t;
   }
   __syncthreads();
 #pragma unroll
-  for (int q = 0; q < kNQ; ++q) v[q] = c.red[q * kWarps];
+  for (int q = 0; q < kNQ; ++q) v[q] = c.red()[q * kWarps];
   __syncthreads();
   c.epoch++;
 }
@@ -223,16 +256,17 @@ __device__ __forceinline__ double cont_point(int egno, bool last_k, double r00, 
 // ---- phase A: residual rows -> y-FFT -> transposed half spectrum ----
 template <int ND, int VW>
 __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
-  const CoopArgs& a = c.a;
+  const CoopArgs& a = cargs();
   const MarchParams& p = a.p;
   const int K = p.K, nx = a.nxe, ny = a.nye, nyh = a.nyh, TR = a.TR;
   const size_t n = (size_t)nx * ny, KN = (size_t)K * n;
   const int rows = K * nx, ntiles = (rows + TR - 1) / TR;
   const int ld = fft_ld(ny);
-  double2* buf0 = c.work;
+  double2* buf0 = c.work();
   double2* buf1 = buf0 + (size_t)(TR / 2) * ld;
-  const double* rho = a.w.rho[cd];
-  const double* al = a.w.alp[cd];
+  const double* rho = as_global(a.w.rho[cd]);
+  const double* al = as_global(a.w.alp[cd]);
+  double2* ztg = as_global(a.w.zt);
   const double* a1x = al;
   const double* a2x = al + KN;
   const double* a1y = al + (size_t)(2 * ND - 2) * KN;
@@ -263,12 +297,12 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
 #pragma unroll
           for (int e = 0; e < VW; ++e) rnext.e[e] = 0.0;
         }
-        const double r_l = rho[o + jm], r_r = rho[o + jq];
+        const double r_l = ldg1(rho + o + jm), r_r = ldg1(rho + o + jq);
         Vec<VW> v1y, v2y;
         double a1y_l = 0.0, a2y_r = 0.0;
         if (egno != 3) {
           v1y = ldv<VW>(a1y + o + j); v2y = ldv<VW>(a2y + o + j);
-          a1y_l = a1y[o + jm]; a2y_r = a2y[o + jq];
+          a1y_l = ldg1(a1y + o + jm); a2y_r = ldg1(a2y + o + jq);
         } else {
 #pragma unroll
           for (int e = 0; e < VW; ++e) { v1y.e[e] = 0.0; v2y.e[e] = 0.0; }
@@ -281,17 +315,17 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
           v1x = ldv<VW>(a1x + o + j); v1xm = ldv<VW>(a1x + om + j);
           v2x = ldv<VW>(a2x + o + j); v2xp = ldv<VW>(a2x + op + j);
         }
-        const double cx0 = (ND == 2 || egno == 3) ? c.cx[i] : 0.0;
-        const double cxm = (ND == 2) ? c.cx[bx.m] : 0.0, cxp = (ND == 2) ? c.cx[bx.p] : 0.0;
+        const double cx0 = (ND == 2 || egno == 3) ? c.cx()[i] : 0.0;
+        const double cxm = (ND == 2) ? c.cx()[bx.m] : 0.0, cxp = (ND == 2) ? c.cx()[bx.p] : 0.0;
 #pragma unroll
         for (int e = 0; e < VW; ++e) {
           const double rym = (e == 0) ? r_l : r00.e[0], ryp = (e == VW - 1) ? r_r : r00.e[VW - 1];
           const double a1m = (e == 0) ? a1y_l : v1y.e[0], a2p = (e == VW - 1) ? a2y_r : v2y.e[VW - 1];
           const int je = j + e;
-          const double cym = c.cy[(e == 0) ? jm : j], cyp = c.cy[(e == VW - 1) ? jq : j + VW - 1];
+          const double cym = c.cy()[(e == 0) ? jm : j], cyp = c.cy()[(e == VW - 1) ? jq : j + VW - 1];
           res.e[e] = cont_point<ND>(egno, k == K - 1, r00.e[e], rnext.e[e], rym, ryp, (ND == 2) ? rxm.e[e] : 0.0, (ND == 2) ? rxp.e[e] : 0.0,
                                     v1y.e[e], a1m, v2y.e[e], a2p, (ND == 2) ? v1x.e[e] : 0.0, (ND == 2) ? v1xm.e[e] : 0.0,
-                                    (ND == 2) ? v2x.e[e] : 0.0, (ND == 2) ? v2xp.e[e] : 0.0, c.cy[je], cym, cyp, cx0, cxm, cxp, bx.wm, bx.wp,
+                                    (ND == 2) ? v2x.e[e] : 0.0, (ND == 2) ? v2xp.e[e] : 0.0, c.cy()[je], cym, cyp, cx0, cxm, cxp, bx.wm, bx.wp,
                                     epsl, rc, c_dt);
         }
       }
@@ -303,7 +337,7 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
     }
     __syncthreads();
     c.tick(0);
-    double2* zf = fft_rows(buf0, buf1, a.plan_ye, ld, c.twy, npairs, 1.0);
+    double2* zf = fft_rows(buf0, buf1, a.plan_ye, ld, c.twy(), npairs, 1.0);
     c.tick(1);
     const float inv_np = 1.0f / (float)npairs;
     for (int idx = tid; idx < npairs * nyh; idx += nth) {
@@ -311,10 +345,10 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
       const int kym = (ky == 0) ? 0 : ny - ky;
       const double2 z1 = zf[(size_t)pr * ld + fpad(ky)], z2 = zf[(size_t)pr * ld + fpad(kym)];
       const int ra = r0 + 2 * pr, ka = fast_div_exact(ra, nx, c.inv_nx), ia = ra - ka * nx;
-      a.w.zt[((size_t)ka * nyh + ky) * nx + ia] = make_double2(0.5 * (z1.x + z2.x), 0.5 * (z1.y - z2.y));
+      stg2(&ztg[((size_t)ka * nyh + ky) * nx + ia], make_double2(0.5 * (z1.x + z2.x), 0.5 * (z1.y - z2.y)));
       if (2 * pr + 1 < nrows) {
         const int rb = ra + 1, kb = fast_div_exact(rb, nx, c.inv_nx), ib = rb - kb * nx;
-        a.w.zt[((size_t)kb * nyh + ky) * nx + ib] = make_double2(0.5 * (z1.y + z2.y), 0.5 * (z2.x - z1.x));
+        stg2(&ztg[((size_t)kb * nyh + ky) * nx + ib], make_double2(0.5 * (z1.y + z2.y), 0.5 * (z2.x - z1.x)));
       }
     }
     __syncthreads();
@@ -326,42 +360,43 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
 __device__ __forceinline__ void thomas_component(double* ztd, const double* den, const double* tu, int K, size_t modes2, size_t w,
                                                  double ct2) {
   const size_t m = w >> 1, modes = modes2 >> 1;
+  ztd = as_global(ztd); den = as_global(den); tu = as_global(tu);
   double bp = 0.0;
   int k = 0;
   for (; k + 4 <= K; k += 4) {      // 4 independent loads ahead of the dependent chain
     double v[4], dn[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { v[q] = ztd[(size_t)(k + q) * modes2 + w]; dn[q] = den[(size_t)(k + q) * modes + m]; }
+    for (int q = 0; q < 4; ++q) { v[q] = ldg1(ztd + (size_t)(k + q) * modes2 + w); dn[q] = ldg1(den + (size_t)(k + q) * modes + m); }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { bp = (v[q] + ct2 * bp) * dn[q]; ztd[(size_t)(k + q) * modes2 + w] = bp; }
+    for (int q = 0; q < 4; ++q) { bp = (v[q] + ct2 * bp) * dn[q]; stg1(ztd + (size_t)(k + q) * modes2 + w, bp); }
   }
   for (; k < K; ++k) {
-    bp = (ztd[(size_t)k * modes2 + w] + ct2 * bp) * den[(size_t)k * modes + m];
-    ztd[(size_t)k * modes2 + w] = bp;
+    bp = (ldg1(ztd + (size_t)k * modes2 + w) + ct2 * bp) * ldg1(den + (size_t)k * modes + m);
+    stg1(ztd + (size_t)k * modes2 + w, bp);
   }
   double xs = bp;
   k = K - 2;
   for (; k - 3 >= 0; k -= 4) {
     double v[4], tv[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { v[q] = ztd[(size_t)(k - q) * modes2 + w]; tv[q] = tu[(size_t)(k - q) * modes + m]; }
+    for (int q = 0; q < 4; ++q) { v[q] = ldg1(ztd + (size_t)(k - q) * modes2 + w); tv[q] = ldg1(tu + (size_t)(k - q) * modes + m); }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { xs = v[q] - tv[q] * xs; ztd[(size_t)(k - q) * modes2 + w] = xs; }
+    for (int q = 0; q < 4; ++q) { xs = v[q] - tv[q] * xs; stg1(ztd + (size_t)(k - q) * modes2 + w, xs); }
   }
   for (; k >= 0; --k) {
-    xs = ztd[(size_t)k * modes2 + w] - tu[(size_t)k * modes + m] * xs;
-    ztd[(size_t)k * modes2 + w] = xs;
+    xs = ldg1(ztd + (size_t)k * modes2 + w) - ldg1(tu + (size_t)k * modes + m) * xs;
+    stg1(ztd + (size_t)k * modes2 + w, xs);
   }
 }
 
 // ---- phase B: x-FFT, t-solve per mode, inverse x-FFT (in place on zt) ----
 __device__ __noinline__ void phase_B(Ctx& c) {
-  const CoopArgs& a = c.a;
+  const CoopArgs& a = cargs();
   const MarchParams& p = a.p;
   const int K = p.K, nx = a.nxe, nyh = a.nyh;
   const int tid = threadIdx.x, nth = blockDim.x;
   const double ct2 = p.Ct_over_dt2;
-  double2* zt = a.w.zt;
+  double2* zt = as_global(a.w.zt);
   const size_t modes = (size_t)nyh * nx;
   const bool coupled = (K > 1 && ct2 != 0.0);
   if (nx == 1) {
@@ -381,7 +416,7 @@ __device__ __noinline__ void phase_B(Ctx& c) {
   }
   const int ld = fft_ld(nx);
   const int TKY = a.TKY;
-  double2* buf0 = c.work;
+  double2* buf0 = c.work();
   double2* buf1 = buf0 + (size_t)TKY * ld;
   const int ntile = (nyh + TKY - 1) / TKY;
   const int nunits = K * ntile;
@@ -392,7 +427,7 @@ __device__ __noinline__ void phase_B(Ctx& c) {
     const int nr = min(TKY, nyh - ky0);
     for (int idx = tid; idx < nr * nx; idx += nth) {
       const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
-      buf0[(size_t)t * ld + fpad(kx)] = zt[((size_t)k * nyh + ky0 + t) * nx + kx];
+      buf0[(size_t)t * ld + fpad(kx)] = ldg2(&zt[((size_t)k * nyh + ky0 + t) * nx + kx]);
     }
     __syncthreads();
     if (p.bc_x == 1) {
@@ -431,21 +466,21 @@ __device__ __noinline__ void phase_B(Ctx& c) {
       __syncthreads();
       continue;
     }
-    double2* zf = fft_rows(buf0, buf1, a.plan_xe, ld, c.twx, nr, 1.0);
+    double2* zf = fft_rows(buf0, buf1, a.plan_xe, ld, c.twx(), nr, 1.0);
     if (!coupled) {
       double2* zo = (zf == buf0) ? buf1 : buf0;
       for (int idx = tid; idx < nr * nx; idx += nth) {
         const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
-        const double rd = 1.0 / (p.diag[(size_t)kx * nyh + ky0 + t] + ((K == 1) ? ct2 : 0.0));
+        const double rd = 1.0 / (ldg1(p.diag + (size_t)kx * nyh + ky0 + t) + ((K == 1) ? ct2 : 0.0));
         const double2 v = zf[(size_t)t * ld + fpad(kx)];
         zf[(size_t)t * ld + fpad(kx)] = make_double2(v.x * rd, v.y * rd);
       }
       __syncthreads();
-      zf = fft_rows(zf, zo, a.plan_xe, ld, c.twx, nr, -1.0);
+      zf = fft_rows(zf, zo, a.plan_xe, ld, c.twx(), nr, -1.0);
     }
     for (int idx = tid; idx < nr * nx; idx += nth) {
       const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
-      zt[((size_t)k * nyh + ky0 + t) * nx + kx] = zf[(size_t)t * ld + fpad(kx)];
+      stg2(&zt[((size_t)k * nyh + ky0 + t) * nx + kx], zf[(size_t)t * ld + fpad(kx)]);
     }
     __syncthreads();
   }
@@ -463,33 +498,36 @@ __device__ __noinline__ void phase_B(Ctx& c) {
     const int nr = min(TKY, nyh - ky0);
     for (int idx = tid; idx < nr * nx; idx += nth) {
       const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
-      buf0[(size_t)t * ld + fpad(kx)] = zt[((size_t)k * nyh + ky0 + t) * nx + kx];
+      buf0[(size_t)t * ld + fpad(kx)] = ldg2(&zt[((size_t)k * nyh + ky0 + t) * nx + kx]);
     }
     __syncthreads();
-    double2* zu = fft_rows(buf0, buf1, a.plan_xe, ld, c.twx, nr, -1.0);
+    double2* zu = fft_rows(buf0, buf1, a.plan_xe, ld, c.twx(), nr, -1.0);
     for (int idx = tid; idx < nr * nx; idx += nth) {
       const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
-      zt[((size_t)k * nyh + ky0 + t) * nx + kx] = zu[(size_t)t * ld + fpad(kx)];
+      stg2(&zt[((size_t)k * nyh + ky0 + t) * nx + kx], zu[(size_t)t * ld + fpad(kx)]);
     }
     __syncthreads();
   }
 }
 
-// ---- phase C: inverse y-FFT, phi update.  CTA partials: slot 15 (sum dphi^2), 16 (sum phi_prev^2 rows>=1), 17 (NaN count)
+// ---- phase C: inverse y-FFT, phi update.  CTA partials: slot 16 (sum dphi^2), 17 (sum phi_prev^2 rows>=1), 18 (NaN count)
 template <int VW>
 __device__ __noinline__ void phase_C(Ctx& c, const double* phi_prev, double* phi_next, double* phib, double tau) {
-  const CoopArgs& a = c.a;
+  const CoopArgs& a = cargs();
   const MarchParams& p = a.p;
   const int K = p.K, nx = a.nxe, ny = a.nye, nyh = a.nyh, TR = a.TR;
   const size_t n = (size_t)nx * ny;
   const int rows = K * nx, ntiles = (rows + TR - 1) / TR;
   const int ld = fft_ld(ny);
-  double2* buf0 = c.work;
+  double2* buf0 = c.work();
   double2* buf1 = buf0 + (size_t)(TR / 2) * ld;
   const int tid = threadIdx.x, nth = blockDim.x;
   const double inv_nn = 1.0 / ((double)nx * (double)ny);
   const int ny2 = ny / VW;
   const int dlr = nth / ny2, djp = nth - dlr * ny2;
+  const double2* ztg = as_global(a.w.zt);
+  phi_prev = as_global(phi_prev); phi_next = as_global(phi_next);
+  if (phib) phib = as_global(phib);
   double s_d = 0.0, s_p = 0.0, s_n = 0.0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int r0 = tile * TR;
@@ -498,11 +536,11 @@ __device__ __noinline__ void phase_C(Ctx& c, const double* phi_prev, double* phi
     for (int idx = tid; idx < npairs * nyh; idx += nth) {
       const int ky = fast_div_exact(idx, npairs, inv_np), pr = idx - ky * npairs;
       const int ra = r0 + 2 * pr, ka = fast_div_exact(ra, nx, c.inv_nx), ia = ra - ka * nx;
-      const double2 ua = a.w.zt[((size_t)ka * nyh + ky) * nx + ia];
+      const double2 ua = ldg2(&ztg[((size_t)ka * nyh + ky) * nx + ia]);
       double2 ub = make_double2(0.0, 0.0);
       if (2 * pr + 1 < nrows) {
         const int rb = ra + 1, kb = fast_div_exact(rb, nx, c.inv_nx), ib = rb - kb * nx;
-        ub = a.w.zt[((size_t)kb * nyh + ky) * nx + ib];
+        ub = ldg2(&ztg[((size_t)kb * nyh + ky) * nx + ib]);
       }
       buf0[(size_t)pr * ld + fpad(ky)] = make_double2(ua.x - ub.y, ua.y + ub.x);
       const int kym = ny - ky;
@@ -510,7 +548,7 @@ __device__ __noinline__ void phase_C(Ctx& c, const double* phi_prev, double* phi
     }
     __syncthreads();
     c.tick(6);
-    double2* zu = fft_rows(buf0, buf1, a.plan_ye, ld, c.twy, npairs, -1.0);
+    double2* zu = fft_rows(buf0, buf1, a.plan_ye, ld, c.twy(), npairs, -1.0);
     c.tick(7);
     int lr = tid / ny2, jp = tid - lr * ny2;
     while (lr < nrows) {
@@ -537,7 +575,7 @@ __device__ __noinline__ void phase_C(Ctx& c, const double* phi_prev, double* phi
     c.tick(8);
   }
   const double sums[3] = {s_d, s_p, s_n};
-  cta_partials<3>(c, sums, 15);
+  cta_partials<3>(c, sums, 16);
 }
 
 // dual update at one point (update_fns_in_pdhg.py:99-133,150-165; set_fns.py prox formulas)
@@ -579,28 +617,30 @@ __device__ __forceinline__ void dual_point(int egno, double c0, double cxm, doub
 }
 
 // ---- phase D: one dual sweep.  src -> dst (may alias); outer differences against `ref` when HASREF.
-// CTA partials: slots 0..1 rho (diff^2, next^2), 2+2q..3+2q alp q; 10 outer rho diff^2, 11+q outer alp diff^2; 18 NaN count of rho_next
-template <int ND, int VW, bool HASREF>
+// CTA partials: slots 0..1 rho (diff^2, next^2), 2+2q..3+2q alp q; 10 outer rho diff^2, 11+q outer alp diff^2; 15 NaN count of rho_next
+template <int ND, int VW, bool HASREF, int EG>
 __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d, double* alp_d,
                         const double* rho_ref, const double* alp_ref, double sigma, double epsl) {
+  phib = as_global(phib); rho_s = as_global(rho_s); alp_s = as_global(alp_s); rho_d = as_global(rho_d); alp_d = as_global(alp_d);
+  if (HASREF) { rho_ref = as_global(rho_ref); alp_ref = as_global(alp_ref); }
   constexpr int NA = 2 * ND;
-  const CoopArgs& a = c.a;
+  const CoopArgs& a = cargs();
   const MarchParams& p = a.p;
-  const int K = p.K, nx = a.nxe, ny = a.nye, egno = p.egno;
+  const int K = p.K, nx = a.nxe, ny = a.nye;
+  constexpr int egno = EG;                 // compile-time problem id: the other prox variants are not even compiled in
   const size_t n = (size_t)nx * ny, KN = (size_t)K * n;
   const Recip rc(p.dt, a.dxe, a.dye, sigma);
-  const int lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  const int ny2 = ny / VW, nchunk = (ny2 + 31) >> 5;
-  const long long units = (long long)K * nx * nchunk;
+  const int ny2 = ny / VW;
   double s_dr = 0.0, s_rr = 0.0, s_or = 0.0, s_nan = 0.0;
   double s_da[NA], s_aa[NA], s_oa[NA];
 #pragma unroll
   for (int q = 0; q < NA; ++q) { s_da[q] = 0.0; s_aa[q] = 0.0; s_oa[q] = 0.0; }
-  for (long long unit = (long long)blockIdx.x * nwarp + (threadIdx.x >> 5); unit < units; unit += (long long)gridDim.x * nwarp) {
-    const int r = (units < (1LL << 24)) ? fast_div_exact((int)unit, nchunk, c.inv_nchunk) : (int)(unit / nchunk);
-    const int ch = (int)(unit - (long long)r * nchunk);
-    const int jp = ch * 32 + lane;
-    if (jp >= ny2) continue;
+  // thread-linear grid-stride over VW-wide items: consecutive threads of a CTA take consecutive items of a row
+  const float inv_ny2 = 1.0f / (float)ny2;
+  const long long items = (long long)K * nx * ny2, istride = (long long)gridDim.x * blockDim.x;
+  for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += istride) {
+    const int r = (items < (1LL << 24)) ? fast_div_exact((int)item, ny2, inv_ny2) : (int)(item / ny2);
+    const int jp = (int)(item - (long long)r * ny2);
     const int k = fast_div_exact(r, nx, c.inv_nx), i = r - k * nx, j = jp * VW;
     const size_t row = (size_t)i * ny, g = (size_t)k * n + row + j;
     const double* pb1 = phib + (size_t)(k + 1) * n;
@@ -614,14 +654,14 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
     Vec<VW> cxm, cxp;
     const Nbr bx = nbr(i, nx, p.bc_x);
     if (ND == 2) { cxm = ldv<VW>(pb1 + (size_t)bx.m * ny + j); cxp = ldv<VW>(pb1 + (size_t)bx.p * ny + j); }
-    const double c_l = pb1[row + jm], c_r = pb1[row + jq];
+    const double c_l = ldg1(pb1 + row + jm), c_r = ldg1(pb1 + row + jq);
     Vec<VW> rref, aref[NA];
     if (HASREF) {
       rref = ldv<VW>(rho_ref + g);
 #pragma unroll
       for (int q = 0; q < NA; ++q) aref[q] = ldv<VW>(alp_ref + (size_t)q * KN + g);
     }
-    const double cx = (ND == 2 || egno == 3) ? c.cx[i] : 0.0;
+    const double cx = (ND == 2 || egno == 3) ? c.cx()[i] : 0.0;
     Vec<VW> rn, an[NA];
 #pragma unroll
     for (int e = 0; e < VW; ++e) {
@@ -630,7 +670,7 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
 #pragma unroll
       for (int q = 0; q < NA; ++q) aoe[q] = ao[q].e[e];
       dual_point<ND>(egno, cc.e[e], (ND == 2) ? cxm.e[e] : 0.0, (ND == 2) ? cxp.e[e] : 0.0, cym, cyp, pk.e[e], ro.e[e], aoe, cx,
-                     c.cy[j + e], bx.wm, bx.wp, sigma, epsl, rc, rne, ane);
+                     c.cy()[j + e], bx.wm, bx.wp, sigma, epsl, rc, rne, ane);
       rn.e[e] = rne;
       double d = rne - ro.e[e];
       s_dr += d * d; s_rr += rne * rne; s_nan += is_nan(rne) ? 1.0 : 0.0;
@@ -647,15 +687,14 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
 #pragma unroll
     for (int q = 0; q < NA; ++q) stv<VW>(alp_d + (size_t)q * KN + g, an[q]);
   }
-  double sums[15];
+  c.tick(5);
+  double sums[16];
 #pragma unroll
-  for (int q = 0; q < 15; ++q) sums[q] = 0.0;
-  sums[0] = s_dr; sums[1] = s_rr; sums[10] = s_or;
+  for (int q = 0; q < 16; ++q) sums[q] = 0.0;
+  sums[0] = s_dr; sums[1] = s_rr; sums[10] = s_or; sums[15] = s_nan;
 #pragma unroll
   for (int q = 0; q < NA; ++q) { sums[2 + 2 * q] = s_da[q]; sums[3 + 2 * q] = s_aa[q]; sums[11 + q] = s_oa[q]; }
-  cta_partials<15>(c, sums, 0);
-  const double sn[1] = {s_nan};
-  cta_partials<1>(c, sn, 18);
+  cta_partials<16>(c, sums, 0);
 }
 
 // ---- phase D, software-pipelined: every warp stages the inputs of its NEXT (row, 64-point chunk) unit in shared memory
@@ -682,9 +721,11 @@ template <int ND> struct DStage {   // doubles per staged unit: cc[64] + 2 halos
 template <int ND, bool HASREF>
 __device__ __noinline__ void phase_D_pipe(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d,
                                           double* alp_d, const double* rho_ref, const double* alp_ref, double sigma, double epsl) {
+  phib = as_global(phib); rho_s = as_global(rho_s); alp_s = as_global(alp_s); rho_d = as_global(rho_d); alp_d = as_global(alp_d);
+  if (HASREF) { rho_ref = as_global(rho_ref); alp_ref = as_global(alp_ref); }
   constexpr int NA = 2 * ND, VW = 2;
   using ST = DStage<ND>;
-  const CoopArgs& a = c.a;
+  const CoopArgs& a = cargs();
   const MarchParams& p = a.p;
   const int K = p.K, nx = a.nxe, ny = a.nye, egno = p.egno;
   const size_t n = (size_t)nx * ny, KN = (size_t)K * n;
@@ -692,7 +733,7 @@ __device__ __noinline__ void phase_D_pipe(Ctx& c, const double* phib, const doub
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int ny2 = ny / VW, nchunk = (ny2 + 31) >> 5;
   const long long units = (long long)K * nx * nchunk, ustride = (long long)gridDim.x * nwarp;
-  double* stage0 = reinterpret_cast<double*>(c.work) + (size_t)warp * 2 * ST::kDoubles;
+  double* stage0 = reinterpret_cast<double*>(c.work()) + (size_t)warp * 2 * ST::kDoubles;
   double s_dr = 0.0, s_rr = 0.0, s_or = 0.0, s_nan = 0.0;
   double s_da[NA], s_aa[NA], s_oa[NA];
 #pragma unroll
@@ -764,7 +805,7 @@ __device__ __noinline__ void phase_D_pipe(Ctx& c, const double* phib, const doub
 #pragma unroll
         for (int t = 0; t < NA; ++t) aref[t] = ldv<VW>(alp_ref + (size_t)t * KN + g);
       }
-      const double cx = (ND == 2 || egno == 3) ? c.cx[i] : 0.0;
+      const double cx = (ND == 2 || egno == 3) ? c.cx()[i] : 0.0;
       Vec<VW> rn, an[NA];
 #pragma unroll
       for (int e = 0; e < VW; ++e) {
@@ -774,7 +815,7 @@ __device__ __noinline__ void phase_D_pipe(Ctx& c, const double* phib, const doub
 #pragma unroll
         for (int t = 0; t < NA; ++t) aoe[t] = e ? ao[t].y : ao[t].x;
         const double roe = e ? ro.y : ro.x;
-        dual_point<ND>(egno, c0, e ? cxm.y : cxm.x, e ? cxp.y : cxp.x, cym, cyp, e ? pk.y : pk.x, roe, aoe, cx, c.cy[j + e], bx.wm,
+        dual_point<ND>(egno, c0, e ? cxm.y : cxm.x, e ? cxp.y : cxp.x, cym, cyp, e ? pk.y : pk.x, roe, aoe, cx, c.cy()[j + e], bx.wm,
                        bx.wp, sigma, epsl, rc, rne, ane);
         rn.e[e] = rne;
         double d = rne - roe;
@@ -796,15 +837,13 @@ __device__ __noinline__ void phase_D_pipe(Ctx& c, const double* phib, const doub
     sidx ^= 1;
   }
   cp_async_wait<0>();
-  double sums[15];
+  double sums[16];
 #pragma unroll
-  for (int q = 0; q < 15; ++q) sums[q] = 0.0;
-  sums[0] = s_dr; sums[1] = s_rr; sums[10] = s_or;
+  for (int q = 0; q < 16; ++q) sums[q] = 0.0;
+  sums[0] = s_dr; sums[1] = s_rr; sums[10] = s_or; sums[15] = s_nan;
 #pragma unroll
   for (int q = 0; q < NA; ++q) { sums[2 + 2 * q] = s_da[q]; sums[3 + 2 * q] = s_aa[q]; sums[11 + q] = s_oa[q]; }
-  cta_partials<15>(c, sums, 0);
-  const double sn[1] = {s_nan};
-  cta_partials<1>(c, sn, 18);
+  cta_partials<16>(c, sums, 0);
 }
 
 // ---- phase E (only after an inner loop of more than one sweep): outer-iteration differences of the dual variables,
@@ -812,7 +851,8 @@ __device__ __noinline__ void phase_D_pipe(Ctx& c, const double* phib, const doub
 // in every extra sweep keeps the extra sweeps at the traffic of the first one.  CTA partials: slot 10 rho, 11+q alp q.
 template <int VW>
 __device__ __noinline__ void phase_E(Ctx& c, const double* rho_n, const double* alp_n, const double* rho_o, const double* alp_o) {
-  const CoopArgs& a = c.a;
+  rho_n = as_global(rho_n); alp_n = as_global(alp_n); rho_o = as_global(rho_o); alp_o = as_global(alp_o);
+  const CoopArgs& a = cargs();
   const size_t KN = (size_t)a.p.K * a.nxe * a.nye;
   const int A = a.A;
   const size_t stride = (size_t)gridDim.x * blockDim.x * VW;
@@ -837,34 +877,42 @@ __device__ __noinline__ void phase_E(Ctx& c, const double* rho_n, const double* 
 
 // runtime -> compile-time dispatch of the templated phases
 __device__ __forceinline__ void run_A(Ctx& c, int cd, double epsl) {
-  const bool v2 = (c.a.nye & 1) == 0;
-  if (c.a.has_x) { if (v2) phase_A<2, 2>(c, cd, epsl); else phase_A<2, 1>(c, cd, epsl); }
+  const bool v2 = (cargs().nye & 1) == 0;
+  if (cargs().has_x) { if (v2) phase_A<2, 2>(c, cd, epsl); else phase_A<2, 1>(c, cd, epsl); }
   else { if (v2) phase_A<1, 2>(c, cd, epsl); else phase_A<1, 1>(c, cd, epsl); }
 }
 __device__ __forceinline__ void run_C(Ctx& c, const double* pp, double* pn, double* pb, double tau) {
-  if ((c.a.nye & 1) == 0) phase_C<2>(c, pp, pn, pb, tau); else phase_C<1>(c, pp, pn, pb, tau);
+  if ((cargs().nye & 1) == 0) phase_C<2>(c, pp, pn, pb, tau); else phase_C<1>(c, pp, pn, pb, tau);
+}
+template <int EG>
+__device__ __forceinline__ void run_D_eg(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d, double* alp_d,
+                                         const double* rho_ref, const double* alp_ref, double sigma, double epsl) {
+  const bool v2 = (cargs().nye & 1) == 0;
+  if (rho_ref) {
+    if (cargs().has_x) { if (v2) phase_D<2, 2, true, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
+                         else phase_D<2, 1, true, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl); }
+    else { if (v2) phase_D<1, 2, true, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
+           else phase_D<1, 1, true, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl); }
+  } else {
+    if (cargs().has_x) { if (v2) phase_D<2, 2, false, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
+                         else phase_D<2, 1, false, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
+    else { if (v2) phase_D<1, 2, false, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
+           else phase_D<1, 1, false, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
+  }
 }
 __device__ __forceinline__ void run_D(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d, double* alp_d,
                                       const double* rho_ref, const double* alp_ref, double sigma, double epsl) {
-  const bool v2 = (c.a.nye & 1) == 0;
-  if (c.a.d_pipe) {
-    if (rho_ref) { if (c.a.has_x) phase_D_pipe<2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
+  if (cargs().d_pipe) {
+    if (rho_ref) { if (cargs().has_x) phase_D_pipe<2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
                    else phase_D_pipe<1, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl); }
-    else { if (c.a.has_x) phase_D_pipe<2, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
+    else { if (cargs().has_x) phase_D_pipe<2, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
            else phase_D_pipe<1, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
     return;
   }
-  if (rho_ref) {
-    if (c.a.has_x) { if (v2) phase_D<2, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
-                     else phase_D<2, 1, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl); }
-    else { if (v2) phase_D<1, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
-           else phase_D<1, 1, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl); }
-  } else {
-    if (c.a.has_x) { if (v2) phase_D<2, 2, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
-                     else phase_D<2, 1, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
-    else { if (v2) phase_D<1, 2, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
-           else phase_D<1, 1, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
-  }
+  const int eg = cargs().p.egno;
+  if (eg == 1) run_D_eg<1>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
+  else if (eg == 2) run_D_eg<2>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
+  else run_D_eg<3>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
 }
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -874,8 +922,9 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 
 __device__ void grid_copy(double* dst, const double* src, size_t count) {
+  dst = as_global(dst); src = as_global(src);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < count; g += stride) dst[g] = src[g];
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < count; g += stride) stg1(dst + g, ldg1(src + g));
 }
 
 // Thomas tables (utils_precond.py:13-27 recurrences for dl = du = -Ct/dt^2, diagonal diag + Ct*[2,..,2,1]/dt^2)
@@ -899,19 +948,17 @@ __device__ void build_tables(const CoopArgs& a) {
 }
 
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const __grid_constant__ CoopArgs a_param) {
-  extern __shared__ __align__(16) double2 dynsm[];
-  __shared__ double red[kNQ * kWarps];
-  // the argument block is referenced from the (non-inlined) phase functions; keep it in shared memory so that it is
-  // neither spilled to a local-memory copy nor lost with every L1 invalidation of a grid sync
-  __shared__ __align__(16) unsigned char a_smem[sizeof(CoopArgs)];
+  // the argument block is referenced from the (non-inlined) phase functions; it lives at the start of shared memory so that
+  // it is neither spilled to a local-memory copy nor lost with every L1 invalidation of a grid sync
   {
     const unsigned int* src = reinterpret_cast<const unsigned int*>(&a_param);
-    unsigned int* dst = reinterpret_cast<unsigned int*>(a_smem);
+    unsigned int* dst = reinterpret_cast<unsigned int*>(g_sm);
     for (int i = threadIdx.x; i < (int)(sizeof(CoopArgs) / 4); i += blockDim.x) dst[i] = src[i];
     __syncthreads();
   }
-  const CoopArgs& a = *reinterpret_cast<const CoopArgs*>(a_smem);
-  Ctx c(a, dynsm, red);
+  const CoopArgs& a = cargs();
+  Ctx c;
+  double* red = c.red();
   const MarchParams& p = a.p;
   const int tid = threadIdx.x, b = a.b;
   const int K = p.K, A = a.A;
@@ -1040,7 +1087,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
           if (j == 0) run_D(c, w.phib, w.rho[cd], w.alp[cd], w.rho[nd], w.alp[nd], nullptr, nullptr, sigma, epsl);
           else run_D(c, w.phib, w.rho[nd], w.alp[nd], w.rho[nd], w.alp[nd], nullptr, nullptr, sigma, epsl);   // in place
           grid_gather(c, v);
-          if (j == 0) { e1s0 = v[15]; e1s1 = v[16]; e1nan = v[17]; }
+          c.tick(9);
+          if (j == 0) { e1s0 = v[16]; e1s1 = v[17]; e1nan = v[18]; }
           double err = v[0] / v[1];
 #pragma unroll
           for (int q = 0; q < 4; ++q) if (q < A) err += v[2 + 2 * q] / v[3 + 2 * q];
@@ -1070,7 +1118,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
         S_rho = v[1];
 #pragma unroll
         for (int q = 0; q < 4; ++q) S_alp[q] = v[3 + 2 * q];
-        const bool anynan = (e1nan > 0.0) || (v[18] > 0.0);
+        const bool anynan = (e1nan > 0.0) || (v[15] > 0.0);
         cp ^= 1; cd = nd;       // accept phi_next, rho_next, alp_next
         if (err1 < p.eps && err2 < p.eps) { reason = END_CONVERGED; break; }
         if (anynan) { reason = END_NAN; break; }
@@ -1086,12 +1134,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
           double* part = w.partials + (size_t)(c.epoch & 1) * gridDim.x * kNQ;
           if (tid == 0) {
             for (int q = 1; q < (int)(blockDim.x >> 5); ++q) { mn = fmin(mn, red[q]); mx = fmax(mx, red[kWarps + q]); }
-            part[(size_t)blockIdx.x * kNQ] = mn; part[(size_t)blockIdx.x * kNQ + 1] = mx;
+            part[blockIdx.x] = mn; part[(size_t)gridDim.x + blockIdx.x] = mx;
           }
           c.grid.sync();
           mn = 1e300; mx = -1e300;
           for (int g = 0; g < (int)gridDim.x; ++g) {
-            mn = fmin(mn, *((volatile double*)&part[(size_t)g * kNQ])); mx = fmax(mx, *((volatile double*)&part[(size_t)g * kNQ + 1]));
+            mn = fmin(mn, *((volatile double*)&part[g])); mx = fmax(mx, *((volatile double*)&part[(size_t)gridDim.x + g]));
           }
           c.epoch++;
           rmin = mn; rmax = mx;
@@ -1168,7 +1216,7 @@ static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   g.nyh = g.nye / 2 + 1;
   const int rows = p.K * g.nxe;
   // y-FFT tile: TR rows (even) -> TR/2 complex transforms, two buffers of (TR/2)*(nye+1) complex
-  const size_t tab = (size_t)24 * (g.nxe + g.nye) + 16;            // twiddles + coefficient tables
+  const size_t tab = (size_t)kArgsBytes + kRedBytes + (size_t)24 * (g.nxe + g.nye) + 32;   // args, reduction scratch, twiddles + coefficient tables
   const size_t cap = smem_cap > tab ? smem_cap - tab : 0;
   int TR = 16;
   while (TR > 2 && ((rows + TR - 1) / TR < 2 * sm_count || (size_t)TR * fft_ld(g.nye) * 16 > cap)) TR -= 2;

@@ -162,7 +162,7 @@ class Solver:
     out = np.zeros(16)
     _check(self.lib.pdhg_phase_times(self._h, _hptr(out)))
     names = ("A_residual_ffty", "B_fftx_tsolve", "C_iffty_phi", "D_dual_reduce", "unused", "setup_records_output",
-             "a_compute", "a_fft", "a_store", "b_pass1", "b_pass2", "b_pass3", "c_load", "c_fft", "c_update", "spare")
+             "a_compute", "a_fft", "a_store", "b_pass1", "b_pass2", "d_compute", "c_load", "c_fft", "c_update", "d_reduce")
     return dict(zip(names, (out / 1e6).tolist()))
 
   def debug_phase(self, phase, pass_mask=7, step=0.05, reps=1):
