@@ -254,7 +254,7 @@ __device__ __forceinline__ double cont_point(int egno, bool last_k, double r00, 
 }
 
 // ---- phase A: residual rows -> y-FFT -> transposed half spectrum ----
-template <int ND, int VW>
+template <int ND, int VW, int EG>
 __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
   const CoopArgs& a = cargs();
   const MarchParams& p = a.p;
@@ -272,7 +272,7 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
   const double* a1y = al + (size_t)(2 * ND - 2) * KN;
   const double* a2y = al + (size_t)(2 * ND - 1) * KN;
   const int tid = threadIdx.x, nth = blockDim.x;
-  const int egno = p.egno;
+  constexpr int egno = EG;
   const Recip rc(p.dt, a.dxe, a.dye, 1.0);
   const double c_dt = p.c_on_rho * rc.idt;
   const int ny2 = ny / VW;
@@ -876,10 +876,15 @@ __device__ __noinline__ void phase_E(Ctx& c, const double* rho_n, const double* 
 }
 
 // runtime -> compile-time dispatch of the templated phases
-__device__ __forceinline__ void run_A(Ctx& c, int cd, double epsl) {
+template <int EG>
+__device__ __forceinline__ void run_A_eg(Ctx& c, int cd, double epsl) {
   const bool v2 = (cargs().nye & 1) == 0;
-  if (cargs().has_x) { if (v2) phase_A<2, 2>(c, cd, epsl); else phase_A<2, 1>(c, cd, epsl); }
-  else { if (v2) phase_A<1, 2>(c, cd, epsl); else phase_A<1, 1>(c, cd, epsl); }
+  if (cargs().has_x) { if (v2) phase_A<2, 2, EG>(c, cd, epsl); else phase_A<2, 1, EG>(c, cd, epsl); }
+  else { if (v2) phase_A<1, 2, EG>(c, cd, epsl); else phase_A<1, 1, EG>(c, cd, epsl); }
+}
+__device__ __forceinline__ void run_A(Ctx& c, int cd, double epsl) {
+  // the continuity residual only distinguishes the Newton example (egno 3: f = [alp, x]) from the a(x)-scaled ones
+  if (cargs().p.egno == 3) run_A_eg<3>(c, cd, epsl); else run_A_eg<1>(c, cd, epsl);
 }
 __device__ __forceinline__ void run_C(Ctx& c, const double* pp, double* pn, double* pb, double tau) {
   if ((cargs().nye & 1) == 0) phase_C<2>(c, pp, pn, pb, tau); else phase_C<1>(c, pp, pn, pb, tau);
