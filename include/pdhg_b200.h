@@ -104,6 +104,25 @@ double pdhg_last_kernel_ms(const pdhg_handle* h);
  * B FFT_x+t-solve, C IFFT_y+phi update, D dual sweeps+reduction, -, setup/records/output}, out16[6..15] = sub-steps seen
  * by CTA 0 (A: compute, fft, store; B: pass 1, 2, 3; C: load, fft, update; spare); zeros on the single-CTA path */
 int pdhg_phase_times(pdhg_handle* h, double* out16);
+/* Slab mode — building block of the multi-GPU x-slab decomposition of ONE large 2-D grid (BASELINE configs[4]; the host
+ * side with the NCCL halo exchange / all-to-all transposes / all-reduce is pdhg_b200/slab.py).  Runs ONE phase of the
+ * cooperative kernel on caller-owned device buffers of a local, ghost-padded slab (null = the handle's workspace):
+ *   phase 0 = A: (rho_in, alp_in) -> zt        continuity residual + y-FFT, half spectrum stored transposed [K][ny/2+1][nx]
+ *   phase 1 = B: zt in place                   x-FFT, per-mode solve, inverse x-FFT; `nyh_override`/`ky_off`/`nyh_tab` select the
+ *                                              ky-slab this rank owns after the transpose (table row length nyh_tab)
+ *   phase 2 = C: (zt, phi_in) -> phi_out, phib inverse y-FFT + phi update (step = tau)
+ *   phase 3 = D: (phib, rho_in, alp_in) -> rho_out, alp_out   one dual sweep (step = sigma); may run in place
+ *   phase 4 = E: outer differences of (rho_out, alp_out) against (rho_in, alp_in)
+ * Rows outside [sum_lo, sum_hi) (ghost rows) do not contribute to the error sums.  Phases 3 and 4 store the grid totals of the
+ * 20 reduced quantities (dual sums in 0..15, the preceding phase C's primal sums in 16..18) to bufs->sums (device). */
+typedef struct pdhg_ext_buffers {
+  double *phi_in, *phi_out, *phib, *rho_in, *alp_in, *rho_out, *alp_out;
+  void* zt;
+  double* sums;
+} pdhg_ext_buffers;
+int pdhg_ext_phase(pdhg_handle* h, int phase, int pass_mask, double step, double epsl, const pdhg_ext_buffers* bufs,
+                   int sum_lo, int sum_hi, int nyh_override, int ky_off, int nyh_tab, void* stream);
+
 /* diagnostic (profiling aid): launches ONE phase of the cooperative kernel `reps` times on the workspace left by the last
  * march, so that ncu sees each phase as its own launch: phase 0 = A, 1 = B (pass_mask bit 0/1/2 = x-FFT / t-solve / inverse
  * x-FFT), 2 = C, 3 = D + reduction; `step` = tau or sigma.  Results are meaningless; caller buffers are not touched. */

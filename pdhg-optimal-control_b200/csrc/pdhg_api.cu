@@ -19,6 +19,8 @@ size_t pdhg1d_cta_smem_bytes(int nx, int K);
 cudaError_t launch_pdhg_coop(const MarchParams& p, int B, void* ws, cudaStream_t stream, long long* launches);
 size_t pdhg_coop_workspace_bytes(const MarchParams& p, int B);
 cudaError_t coop_phase_times(const MarchParams& p, void* ws, double* out6);
+cudaError_t launch_ext_phase(const MarchParams& p, void* ws, int phase, int pass_mask, double step, const ExtPhaseDesc& ext,
+                             cudaStream_t stream);
 cudaError_t launch_debug_phase(const MarchParams& p, void* ws, int phase, int pass_mask, double step, cudaStream_t stream);
 cudaError_t launch_pack_alp(const double* ref_layout, double* planar, int B, int A, size_t kn, int n_ctrl, int ndim,
                             int egno, int to_planar, cudaStream_t stream);
@@ -66,6 +68,8 @@ struct pdhg_handle {
   int* n_inner = nullptr;
   double* err_inner = nullptr;
   double* dbg_ns = nullptr;
+  double ext_epsl = 0.0;
+  bool ext_epsl_set = false;
   void* ws = nullptr;         // cooperative-kernel workspace
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the solver kernel(s) of the last march on its stream
   bool ev_valid = false;
@@ -148,6 +152,7 @@ extern "C" double pdhg_last_kernel_ms(const pdhg_handle* h) {
 extern "C" int64_t pdhg_launch_count(const pdhg_handle* h) { return h ? h->launches : 0; }
 
 static void fill_params(pdhg_handle* h, MarchParams* p);
+static int upload_scalars(pdhg_handle* h, const double* epsl_host, const double* stepsz_host, cudaStream_t s);
 
 extern "C" int pdhg_phase_times(pdhg_handle* h, double* out6 /* 16 doubles */) {
   if (!h || !out6) return fail(PDHG_ERR_ARG, "pdhg_phase_times: null argument");
@@ -161,6 +166,27 @@ extern "C" int pdhg_phase_times(pdhg_handle* h, double* out6 /* 16 doubles */) {
   fill_params(h, &p);
   CU(cudaSetDevice(h->cfg.device));
   CU(coop_phase_times(p, h->ws, out6));
+  return PDHG_OK;
+}
+
+extern "C" int pdhg_ext_phase(pdhg_handle* h, int phase, int pass_mask, double step, double epsl, const pdhg_ext_buffers* bufs,
+                              int sum_lo, int sum_hi, int nyh_override, int ky_off, int nyh_tab, void* stream) {
+  if (!h || !bufs || phase < 0 || phase > 4) return fail(PDHG_ERR_ARG, "pdhg_ext_phase: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->ext_epsl != epsl || !h->ext_epsl_set) {
+    int rc = upload_scalars(h, &epsl, nullptr, s);
+    if (rc) return rc;
+    h->ext_epsl = epsl; h->ext_epsl_set = true;
+  }
+  MarchParams p;
+  fill_params(h, &p);
+  ExtPhaseDesc e;
+  e.phi_in = bufs->phi_in; e.phi_out = bufs->phi_out; e.phib = bufs->phib; e.rho_in = bufs->rho_in; e.alp_in = bufs->alp_in;
+  e.rho_out = bufs->rho_out; e.alp_out = bufs->alp_out; e.zt = bufs->zt; e.sums = bufs->sums;
+  e.sum_lo = sum_lo; e.sum_hi = sum_hi; e.nyh_override = nyh_override; e.ky_off = ky_off; e.nyh_tab = nyh_tab;
+  CU(launch_ext_phase(p, h->ws, phase, pass_mask, step, e, s));
+  h->launches += 1;
   return PDHG_OK;
 }
 

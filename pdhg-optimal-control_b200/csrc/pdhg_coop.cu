@@ -58,6 +58,9 @@ struct CoopArgs {
   int nyh;            // nye/2 + 1
   int TR, TKY;        // rows per y-FFT tile (even), ky rows per x-FFT tile
   int has_x;          // 0 for a 1-D problem
+  int sum_lo, sum_hi;        // x-rows that contribute to the error sums (slab mode: ghost rows excluded); default [0, nxe)
+  int ky_off, nyh_tab;       // phase B on an exchanged ky-slab: offset and row length of the per-mode table; default 0, nyh
+  double* ext_sums;          // MODE_PHASE: device array [kNQ] receiving the grid totals of phases D / E (may be null)
   int dbg_phase, dbg_pass;   // MODE_PHASE (profiling): phase id 0..3 = A,B,C,D and pass mask of phase B (bit 0,1,2)
   int d_pipe;         // 1: cp.async-pipelined dual sweep (ny even and the staging buffers fit shared memory)
   double dxe, dye;
@@ -445,7 +448,7 @@ __device__ __noinline__ void phase_B(Ctx& c) {
           sx += v.x * cv; sy += v.y * cv;
           m += 2 * kx; if (m >= m4) m -= m4; if (m >= m4) m -= m4;
         }
-        const double rd = 1.0 / (p.diag[(size_t)kx * nyh + ky0 + t] + ct2);
+        const double rd = 1.0 / (p.diag[(size_t)kx * a.nyh_tab + a.ky_off + ky0 + t] + ct2);
         buf1[(size_t)t * ld + fpad(kx)] = make_double2(2.0 * sx * rd, 2.0 * sy * rd);
       }
       __syncthreads();
@@ -471,7 +474,7 @@ __device__ __noinline__ void phase_B(Ctx& c) {
       double2* zo = (zf == buf0) ? buf1 : buf0;
       for (int idx = tid; idx < nr * nx; idx += nth) {
         const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
-        const double rd = 1.0 / (ldg1(p.diag + (size_t)kx * nyh + ky0 + t) + ((K == 1) ? ct2 : 0.0));
+        const double rd = 1.0 / (ldg1(p.diag + (size_t)kx * a.nyh_tab + a.ky_off + ky0 + t) + ((K == 1) ? ct2 : 0.0));
         const double2 v = zf[(size_t)t * ld + fpad(kx)];
         zf[(size_t)t * ld + fpad(kx)] = make_double2(v.x * rd, v.y * rd);
       }
@@ -563,7 +566,7 @@ __device__ __noinline__ void phase_C(Ctx& c, const double* phi_prev, double* phi
         const double u = zsrc[2 * e] * inv_nn;
         pn.e[e] = pp.e[e] + tau * u;
         const double df = pn.e[e] - pp.e[e];
-        s_d += df * df; s_p += pp.e[e] * pp.e[e]; s_n += is_nan(pn.e[e]) ? 1.0 : 0.0;
+        if (i >= a.sum_lo && i < a.sum_hi) { s_d += df * df; s_p += pp.e[e] * pp.e[e]; s_n += is_nan(pn.e[e]) ? 1.0 : 0.0; }
         pb.e[e] = 2 * pn.e[e] - pp.e[e];
       }
       stv<VW>(phi_next + g, pn);
@@ -662,6 +665,7 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
       for (int q = 0; q < NA; ++q) aref[q] = ldv<VW>(alp_ref + (size_t)q * KN + g);
     }
     const double cx = (ND == 2 || egno == 3) ? c.cx()[i] : 0.0;
+    const bool acc_on = (i >= a.sum_lo && i < a.sum_hi);
     Vec<VW> rn, an[NA];
 #pragma unroll
     for (int e = 0; e < VW; ++e) {
@@ -672,15 +676,18 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
       dual_point<ND>(egno, cc.e[e], (ND == 2) ? cxm.e[e] : 0.0, (ND == 2) ? cxp.e[e] : 0.0, cym, cyp, pk.e[e], ro.e[e], aoe, cx,
                      c.cy()[j + e], bx.wm, bx.wp, sigma, epsl, rc, rne, ane);
       rn.e[e] = rne;
-      double d = rne - ro.e[e];
-      s_dr += d * d; s_rr += rne * rne; s_nan += is_nan(rne) ? 1.0 : 0.0;
-      if (HASREF) { d = rne - rref.e[e]; s_or += d * d; }
 #pragma unroll
-      for (int q = 0; q < NA; ++q) {
-        an[q].e[e] = ane[q];
-        d = ane[q] - aoe[q];
-        s_da[q] += d * d; s_aa[q] += ane[q] * ane[q];
-        if (HASREF) { d = ane[q] - aref[q].e[e]; s_oa[q] += d * d; }
+      for (int q = 0; q < NA; ++q) an[q].e[e] = ane[q];
+      if (acc_on) {
+        double d = rne - ro.e[e];
+        s_dr += d * d; s_rr += rne * rne; s_nan += is_nan(rne) ? 1.0 : 0.0;
+        if (HASREF) { d = rne - rref.e[e]; s_or += d * d; }
+#pragma unroll
+        for (int q = 0; q < NA; ++q) {
+          d = ane[q] - aoe[q];
+          s_da[q] += d * d; s_aa[q] += ane[q] * ane[q];
+          if (HASREF) { d = ane[q] - aref[q].e[e]; s_oa[q] += d * d; }
+        }
       }
     }
     stv<VW>(rho_d + g, rn);
@@ -857,7 +864,10 @@ __device__ __noinline__ void phase_E(Ctx& c, const double* rho_n, const double* 
   const int A = a.A;
   const size_t stride = (size_t)gridDim.x * blockDim.x * VW;
   double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  const int ny_ = a.nye, nx_ = a.nxe;
   for (size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VW; g < KN; g += stride) {
+    const int i_ = (int)((g / ny_) % nx_);
+    if (i_ < a.sum_lo || i_ >= a.sum_hi) continue;
     {
       const Vec<VW> x = ldv<VW>(rho_n + g), y = ldv<VW>(rho_o + g);
 #pragma unroll
@@ -986,7 +996,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
       case 0: run_A(c, 0, epsl); break;
       case 1: phase_B(c); break;
       case 2: run_C(c, w.phi[0], w.phi[1], w.phib, a.op_step); break;
-      default: run_D(c, w.phib, w.rho[0], w.alp[0], w.rho[1], w.alp[1], nullptr, nullptr, a.op_step, epsl); grid_gather(c, v); break;
+      case 3: run_D(c, w.phib, w.rho[0], w.alp[0], w.rho[1], w.alp[1], nullptr, nullptr, a.op_step, epsl); grid_gather(c, v); break;
+      default:
+        if ((a.nye & 1) == 0) phase_E<2>(c, w.rho[1], w.alp[1], w.rho[0], w.alp[0]); else phase_E<1>(c, w.rho[1], w.alp[1], w.rho[0], w.alp[0]);
+        grid_gather(c, v);
+        break;
+    }
+    // grid totals of this launch's reduction (incl. the partials a preceding phase-C launch left in slots 16..18) for the
+    // host: slab mode all-reduces them across ranks and takes the decisions there
+    if (a.ext_sums && a.dbg_phase >= 3 && lead) {
+      for (int q = 0; q < kNQ; ++q) a.ext_sums[q] = v[q];
     }
     return;
   }
@@ -1270,9 +1289,23 @@ static CoopWs carve(const MarchParams& p, void* ws) {
   return w;
 }
 
+static void apply_ext(const ExtPhaseDesc& e, CoopArgs& a) {
+  a.ext_sums = e.sums;
+  if (e.phi_in) a.w.phi[0] = e.phi_in;
+  if (e.phi_out) a.w.phi[1] = e.phi_out;
+  if (e.phib) a.w.phib = e.phib;
+  if (e.rho_in) a.w.rho[0] = e.rho_in;
+  if (e.alp_in) a.w.alp[0] = e.alp_in;
+  if (e.rho_out) a.w.rho[1] = e.rho_out;
+  if (e.alp_out) a.w.alp[1] = e.alp_out;
+  if (e.zt) a.w.zt = static_cast<double2*>(e.zt);
+  a.sum_lo = e.sum_lo; a.sum_hi = e.sum_hi;
+  if (e.nyh_override > 0) { a.nyh = e.nyh_override; a.ky_off = e.ky_off; a.nyh_tab = e.nyh_tab; }
+}
+
 static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, const double* op_in, double* op_out,
                                double op_step, double op_eps, int* op_ninner, double* op_err, cudaStream_t stream,
-                               int dbg_phase = 0, int dbg_pass = 7) {
+                               int dbg_phase = 0, int dbg_pass = 7, const ExtPhaseDesc* ext = nullptr) {
   int dev = 0, sms = 0, smem_cap = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -1295,6 +1328,8 @@ static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, 
     a.plan_xe = p.plan_x; a.plan_ye = p.plan_y;
   }
   a.dbg_phase = dbg_phase; a.dbg_pass = dbg_pass;
+  a.sum_lo = 0; a.sum_hi = g.nxe; a.ky_off = 0; a.nyh_tab = g.nyh;
+  if (ext) apply_ext(*ext, a);
   a.op_phi_in = op_in; a.op_phi_out = op_out; a.op_step = op_step; a.op_eps = op_eps; a.op_ninner = op_ninner; a.op_err = op_err;
   e = cudaFuncSetAttribute(pdhg_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return e;
@@ -1311,6 +1346,11 @@ static cudaError_t ensure_tables(const MarchParams& p, void* ws, cudaStream_t st
 
 cudaError_t launch_debug_phase(const MarchParams& p, void* ws, int phase, int pass_mask, double step, cudaStream_t stream) {
   return coop_launch(p, ws, 0, MODE_PHASE, nullptr, nullptr, step, 0.0, nullptr, nullptr, stream, phase, pass_mask);
+}
+
+cudaError_t launch_ext_phase(const MarchParams& p, void* ws, int phase, int pass_mask, double step, const ExtPhaseDesc& ext,
+                             cudaStream_t stream) {
+  return coop_launch(p, ws, 0, MODE_PHASE, nullptr, nullptr, step, 0.0, nullptr, nullptr, stream, phase, pass_mask, &ext);
 }
 
 cudaError_t coop_phase_times(const MarchParams& p, void* ws, double* out6) {

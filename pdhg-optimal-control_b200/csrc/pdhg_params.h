@@ -69,4 +69,13 @@ struct MarchParams {
   double* dbg_ns;                  // [16] diagnostic: clock cycles per sub-step of instance 0 (single-CTA kernel); may be null
 };
 
+// Slab mode (multi-GPU x-slab decomposition): one phase of the cooperative kernel on CALLER-owned buffers of a local,
+// ghost-padded slab (see pdhg_ext_phase in include/pdhg_b200.h).  Null pointers keep the handle's own workspace.
+struct ExtPhaseDesc {
+  double *phi_in, *phi_out, *phib, *rho_in, *alp_in, *rho_out, *alp_out;
+  void* zt;
+  double* sums;
+  int sum_lo, sum_hi, nyh_override, ky_off, nyh_tab;
+};
+
 }  // namespace pdhg

@@ -17,7 +17,7 @@ INST_OK, INST_SOL_NAN, INST_PAUSED, INST_LOG_OVERFLOW = 0, 1, 3, 4
 END_CONVERGED, END_NAN, END_MAXITER, END_PAUSED = 0, 1, 2, 3
 LOG_COLS = 4
 
-EXPORTS = ("pdhg_create", "pdhg_destroy", "pdhg_last_error", "pdhg_path", "pdhg_launch_count", "pdhg_last_kernel_ms", "pdhg_phase_times", "pdhg_debug_phase", "pdhg_update_primal",
+EXPORTS = ("pdhg_create", "pdhg_destroy", "pdhg_last_error", "pdhg_path", "pdhg_launch_count", "pdhg_last_kernel_ms", "pdhg_phase_times", "pdhg_debug_phase", "pdhg_ext_phase", "pdhg_update_primal",
            "pdhg_update_dual", "pdhg_solve_block", "pdhg_multi_step", "pdhg_multi_step_host")
 
 
@@ -34,6 +34,11 @@ class Config(C.Structure):
               ("C", C.c_double), ("pow", C.c_double), ("Ct", C.c_double), ("eps", C.c_double),
               ("rho_alp_iters", C.c_int32), ("batch", C.c_int32), ("nblocks", C.c_int32), ("max_rec", C.c_int32),
               ("device", C.c_int32), ("path", C.c_int32)]
+
+
+class ExtBuffers(C.Structure):
+  _fields_ = [("phi_in", C.c_void_p), ("phi_out", C.c_void_p), ("phib", C.c_void_p), ("rho_in", C.c_void_p), ("alp_in", C.c_void_p),
+              ("rho_out", C.c_void_p), ("alp_out", C.c_void_p), ("zt", C.c_void_p), ("sums", C.c_void_p)]
 
 
 class Logs(C.Structure):
@@ -68,6 +73,8 @@ def load():
   lib.pdhg_phase_times.argtypes = [vp, dp]
   lib.pdhg_debug_phase.restype = C.c_int
   lib.pdhg_debug_phase.argtypes = [vp, C.c_int, C.c_int, dbl, C.c_int]
+  lib.pdhg_ext_phase.restype = C.c_int
+  lib.pdhg_ext_phase.argtypes = [vp, C.c_int, C.c_int, dbl, dbl, C.POINTER(ExtBuffers), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
   lib.pdhg_launch_count.restype = i64
   lib.pdhg_launch_count.argtypes = [vp]
   lib.pdhg_update_primal.restype = C.c_int
@@ -164,6 +171,12 @@ class Solver:
     names = ("A_residual_ffty", "B_fftx_tsolve", "C_iffty_phi", "D_dual_reduce", "unused", "setup_records_output",
              "a_compute", "a_fft", "a_store", "b_pass1", "b_pass2", "d_compute", "c_load", "c_fft", "c_update", "d_reduce")
     return dict(zip(names, (out / 1e6).tolist()))
+
+  def ext_phase(self, phase, step, epsl, sum_lo, sum_hi, stream=None, pass_mask=7, nyh_override=0, ky_off=0, nyh_tab=0, **bufs):
+    """One phase of the cooperative kernel on caller-owned device buffers (ints from `tensor.data_ptr()`); slab mode."""
+    eb = ExtBuffers(*[bufs.get(f[0]) for f in ExtBuffers._fields_])
+    _check(self.lib.pdhg_ext_phase(self._h, int(phase), int(pass_mask), float(step), float(epsl), C.byref(eb), int(sum_lo), int(sum_hi),
+                                   int(nyh_override), int(ky_off), int(nyh_tab), stream))
 
   def debug_phase(self, phase, pass_mask=7, step=0.05, reps=1):
     _check(self.lib.pdhg_debug_phase(self._h, int(phase), int(pass_mask), float(step), int(reps)))

@@ -1,0 +1,273 @@
+"""x-slab decomposition of ONE large 2-D grid over P GPUs (BASELINE configs[4]).
+
+Every rank owns nx/P consecutive x-rows (all y, all t-rows of the block) plus one ghost row on each side.  One outer PDHG
+iteration (jaxsrc/utils/utils_pdhg_solver.py:51-88) becomes
+    halo(rho, alp1_x, alp2_x) -> A (residual + y-FFT) -> all-to-all transpose (ky-slabs) -> B (x-FFT, per-mode solve,
+    inverse x-FFT) -> all-to-all back -> C (inverse y-FFT, phi update) -> halo(phi_bar) -> D (dual sweeps), each sweep
+    followed by ONE small all-reduce of the 20 error sums; the exit tests of the reference run on the host on those sums.
+The phases are the cooperative kernel's own (`pdhg_ext_phase`, caller-owned buffers); the exchange steps are
+torch.distributed collectives (NCCL on GPUs): `all_to_all_single` for the FFT transposes, `all_reduce` for the sums,
+batched point-to-point sends for the halo rows.  `LocalGroup` runs the same algorithm with P emulated ranks inside one
+process on one GPU (tensor copies instead of collectives) — that is how the decomposition is parity-tested without a
+multi-GPU box.  Restrictions of this first version: 2-D, periodic, time_step_per_PDHG = 2 (K = 1), nx divisible by P.
+"""
+import numpy as np
+
+from . import _dev, _lib
+from .set_fns import coef_tables
+
+NQ = 20
+
+
+class SlabRank:
+  """Buffers and handles of one rank."""
+
+  def __init__(self, rank, P, fns_dict, nx, ny, dt, dspatial, c_on_rho, x_arr, C=1.0, eps=1e-6, device=0):
+    t = _dev.require_cuda()
+    assert fns_dict.ndim == 2 and nx % P == 0 and ny % 2 == 0
+    self.rank, self.P, self.nx, self.ny, self.K = rank, P, nx, ny, 1
+    self.nxl = nx // P
+    self.nxp = self.nxl + 2
+    self.nyh = ny // 2 + 1
+    self.kyl = (self.nyh + P - 1) // P
+    self.ky0 = min(rank * self.kyl, self.nyh)
+    self.kyn = max(0, min(self.kyl, self.nyh - self.ky0))      # ky rows this rank owns after the transpose
+    self.dev = t.device("cuda", device)
+    self.eps = eps
+    cx, cy = coef_tables(fns_dict.egno, 2, np.asarray(x_arr))
+    i0 = rank * self.nxl
+    idx = (np.arange(-1, self.nxl + 1) + i0) % nx              # global x index of every local (ghost-padded) row
+    self.i0 = i0
+    dx, dy = float(dspatial[0]), float(dspatial[1])
+    # local handle: the padded slab treated as a small periodic problem (its wrap only touches the ghost rows)
+    self.hL = _lib.Solver(2, fns_dict.egno, self.nxp, ny, 1, fns_dict.n_ctrl, (0, 0), float(dt), dx, dy, float(c_on_rho), cx[idx], cy,
+                          float(C), 1.0, 1.0, float(eps), 10, 1, 1, 4, device, 2)
+    # global handle: owns the per-mode table of the full grid; phase B runs on this rank's ky-slab of it
+    self.hB = _lib.Solver(2, fns_dict.egno, nx, ny, 1, fns_dict.n_ctrl, (0, 0), float(dt), dx, dy, float(c_on_rho), cx, cy,
+                          float(C), 1.0, 1.0, float(eps), 10, 1, 1, 4, device, 2)
+    f64, c128 = t.float64, t.complex128
+    z = lambda *sh: t.zeros(sh, dtype=f64, device=self.dev)
+    self.phi = [z(2, self.nxp, ny), z(2, self.nxp, ny)]
+    self.phib = z(2, self.nxp, ny)
+    self.rho = [z(1, self.nxp, ny), z(1, self.nxp, ny)]
+    self.alp = [z(4, 1, self.nxp, ny), z(4, 1, self.nxp, ny)]
+    self.zt = t.zeros((1, self.nyh, self.nxp), dtype=c128, device=self.dev)
+    self.ztB = t.zeros((1, max(self.kyl, 1), nx), dtype=c128, device=self.dev)
+    self.sums = z(NQ)
+    self.cp, self.cd = 0, 0
+
+  def interior(self, a):
+    return a[..., 1:self.nxl + 1, :]
+
+  def ext(self, h, phase, step, epsl, **kw):
+    ptr = {k: (v.data_ptr() if v is not None else None) for k, v in kw.items() if k not in ("nyh_override", "ky_off", "nyh_tab")}
+    extra = {k: v for k, v in kw.items() if k in ("nyh_override", "ky_off", "nyh_tab")}
+    h.ext_phase(phase, step, epsl, 1, self.nxl + 1, stream=_dev.stream_ptr(self.dev.index), **extra, **ptr)
+
+
+class LocalGroup:
+  """P emulated ranks in one process / on one GPU: collectives are tensor copies (used for parity tests)."""
+
+  def __init__(self, ranks):
+    self.ranks = ranks
+    self.P = len(ranks)
+
+  def halo(self, get):
+    P = self.P
+    for r, R in enumerate(self.ranks):
+      for a, left, right in zip(get(R), get(self.ranks[(r - 1) % P]), get(self.ranks[(r + 1) % P])):
+        a[..., 0, :] = left[..., R.nxl, :]
+        a[..., R.nxl + 1, :] = right[..., 1, :]
+
+  def transpose_fwd(self):
+    t = _dev.torch()
+    P, R0 = self.P, self.ranks[0]
+    K, kyl, nxl, nyh = R0.K, R0.kyl, R0.nxl, R0.nyh
+    send = []
+    for R in self.ranks:
+      z = t.zeros((K, P * kyl, nxl), dtype=R.zt.dtype, device=R.dev)
+      z[:, :nyh] = R.zt[:, :, 1:nxl + 1]
+      send.append(z.view(K, P, kyl, nxl).permute(1, 0, 2, 3).contiguous())          # [dest][K][kyl][nxl]
+    for d, R in enumerate(self.ranks):
+      recv = t.stack([send[s][d] for s in range(P)], dim=0)                           # [src][K][kyl][nxl]
+      R.ztB.copy_(recv.permute(1, 2, 0, 3).reshape(K, kyl, P * nxl))
+
+  def transpose_bwd(self):
+    t = _dev.torch()
+    P, R0 = self.P, self.ranks[0]
+    K, kyl, nxl, nyh = R0.K, R0.kyl, R0.nxl, R0.nyh
+    send = [R.ztB.view(K, kyl, P, nxl).permute(2, 0, 1, 3).contiguous() for R in self.ranks]   # [dest][K][kyl][nxl]
+    for d, R in enumerate(self.ranks):
+      recv = t.stack([send[s][d] for s in range(P)], dim=0)                           # [src = owner of the ky range][K][kyl][nxl]
+      R.zt[:, :, 1:nxl + 1] = recv.permute(1, 0, 2, 3).reshape(K, P * kyl, nxl)[:, :nyh]
+
+  def allreduce(self, vecs):
+    tot = sum(v.clone() for v in vecs)
+    return [tot.clone() for _ in vecs]
+
+  def allreduce_sums(self):
+    tot = sum(R.sums.clone() for R in self.ranks)
+    return tot.cpu().numpy()
+
+
+class DistGroup:
+  """One real rank per process; torch.distributed (NCCL) collectives."""
+
+  def __init__(self, rank_state, dist):
+    self.ranks = [rank_state]
+    self.dist = dist
+    self.P = dist.get_world_size()
+
+  def halo(self, get):
+    t = _dev.torch()
+    dist, R = self.dist, self.ranks[0]
+    P, r = self.P, R.rank
+    left, right = (r - 1) % P, (r + 1) % P
+    ops, pend = [], []
+    for a in get(R):
+      s_first, s_last = a[..., 1, :].contiguous(), a[..., R.nxl, :].contiguous()
+      g_left, g_right = t.empty_like(s_first), t.empty_like(s_first)
+      ops += [dist.P2POp(dist.isend, s_first, left), dist.P2POp(dist.isend, s_last, right),
+              dist.P2POp(dist.irecv, g_left, left), dist.P2POp(dist.irecv, g_right, right)]
+      pend.append((a, g_left, g_right))
+    if P == 1:
+      for a, _, _ in pend:
+        a[..., 0, :] = a[..., R.nxl, :]
+        a[..., R.nxl + 1, :] = a[..., 1, :]
+      return
+    for w in dist.batch_isend_irecv(ops):
+      w.wait()
+    for a, g_left, g_right in pend:
+      a[..., 0, :] = g_left
+      a[..., R.nxl + 1, :] = g_right
+
+  def _a2a(self, send):
+    t = _dev.torch()
+    recv = t.empty_like(send)
+    self.dist.all_to_all_single(t.view_as_real(recv), t.view_as_real(send))
+    return recv
+
+  def transpose_fwd(self):
+    t = _dev.torch()
+    R, P = self.ranks[0], self.P
+    K, kyl, nxl, nyh = R.K, R.kyl, R.nxl, R.nyh
+    z = t.zeros((K, P * kyl, nxl), dtype=R.zt.dtype, device=R.dev)
+    z[:, :nyh] = R.zt[:, :, 1:nxl + 1]
+    recv = self._a2a(z.view(K, P, kyl, nxl).permute(1, 0, 2, 3).contiguous())
+    R.ztB.copy_(recv.permute(1, 2, 0, 3).reshape(K, kyl, P * nxl))
+
+  def transpose_bwd(self):
+    R, P = self.ranks[0], self.P
+    K, kyl, nxl, nyh = R.K, R.kyl, R.nxl, R.nyh
+    recv = self._a2a(R.ztB.view(K, kyl, P, nxl).permute(2, 0, 1, 3).contiguous())
+    R.zt[:, :, 1:nxl + 1] = recv.permute(1, 0, 2, 3).reshape(K, P * kyl, nxl)[:, :nyh]
+
+  def allreduce(self, vecs):
+    self.dist.all_reduce(vecs[0])
+    return vecs
+
+  def allreduce_sums(self):
+    R = self.ranks[0]
+    self.dist.all_reduce(R.sums)
+    return R.sums.cpu().numpy()
+
+
+def init_block(group, g_global, c_on_rho):
+  """phi0 = tile(g), rho0 = c_on_rho, alp0 = 0 on every rank's slab (utils_pdhg_solver.py:123-137)."""
+  t = _dev.torch()
+  for R in group.ranks:
+    gl = t.from_numpy(np.ascontiguousarray(g_global[R.i0:R.i0 + R.nxl])).to(R.dev)
+    for buf in R.phi + [R.phib]:
+      buf.zero_()
+      buf[:, 1:R.nxl + 1, :] = gl
+    for b in R.rho:
+      b.fill_(float(c_on_rho))
+    for b in R.alp:
+      b.zero_()
+    R.cp, R.cd = 0, 0
+  group.halo(lambda R: R.phi + [R.phib])
+
+
+def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_iters=10):
+  """PDHG_solver_oneiter (utils_pdhg_solver.py:9-94) on the slab-decomposed block.  Returns (iters, end_reason, err1, err2, n_inner)."""
+  t = _dev.torch()
+  tau, sigma = stepsz_param / 1.5, stepsz_param * 1.5
+  ranks = group.ranks
+  # norms of the starting iterate (interior rows), all-reduced
+  loc = []
+  for R in ranks:
+    it_ = R.interior
+    v = t.stack([(it_(R.phi[R.cp])[0] ** 2).sum(), (it_(R.rho[R.cd]) ** 2).sum()] +
+                [(it_(R.alp[R.cd][q]) ** 2).sum() for q in range(4)])
+    loc.append(v)
+  tot = group.allreduce(loc)[0].cpu().numpy()
+  S_row0, S_rho, S_alp = tot[0], tot[1], tot[2:6].copy()
+  n_inner, reason, err1, err2 = 0, _lib.END_MAXITER, float("nan"), float("nan")
+  it = 0
+  for it in range(n_maxiter):
+    group.halo(lambda R: [R.rho[R.cd], R.alp[R.cd][0], R.alp[R.cd][1]])
+    for R in ranks:
+      R.ext(R.hL, 0, 0.0, epsl, rho_in=R.rho[R.cd], alp_in=R.alp[R.cd], zt=R.zt)
+    group.transpose_fwd()
+    for R in ranks:
+      if R.kyn > 0:
+        R.ext(R.hB, 1, 0.0, epsl, zt=R.ztB, nyh_override=R.kyn, ky_off=R.ky0, nyh_tab=R.nyh)
+    group.transpose_bwd()
+    for R in ranks:
+      R.ext(R.hL, 2, tau, epsl, zt=R.zt, phi_in=R.phi[R.cp], phi_out=R.phi[R.cp ^ 1], phib=R.phib)
+    group.halo(lambda R: [R.phib])
+    j = 0
+    while j < rho_alp_iters:
+      for R in ranks:
+        nd = R.cd ^ 1
+        src_r, src_a = (R.rho[R.cd], R.alp[R.cd]) if j == 0 else (R.rho[nd], R.alp[nd])
+        R.ext(R.hL, 3, sigma, epsl, phib=R.phib, rho_in=src_r, alp_in=src_a, rho_out=R.rho[nd], alp_out=R.alp[nd], sums=R.sums)
+      v = group.allreduce_sums()
+      if j == 0:
+        e1s0, e1s1, e1nan = v[16], v[17], v[18]
+      j += 1
+      with np.errstate(all="ignore"):
+        err = v[0] / v[1] + sum(v[2 + 2 * q] / v[3 + 2 * q] for q in range(4))
+      if err < eps:
+        break
+    n_inner += j
+    d_rho, d_alp = v[0], [v[2 + 2 * q] for q in range(4)]
+    if j > 1:
+      for R in ranks:
+        nd = R.cd ^ 1
+        R.ext(R.hL, 4, 0.0, epsl, rho_in=R.rho[R.cd], alp_in=R.alp[R.cd], rho_out=R.rho[nd], alp_out=R.alp[nd], sums=R.sums)
+      vo = group.allreduce_sums()
+      d_rho, d_alp = vo[10], [vo[11 + q] for q in range(4)]
+    with np.errstate(all="ignore"):
+      err1 = np.sqrt(e1s0) / np.sqrt(S_row0 + e1s1)
+      err2 = np.sqrt(d_rho) / np.sqrt(S_rho)
+      for q in range(4):
+        na, ne = np.sqrt(S_alp[q]), np.sqrt(d_alp[q])
+        if na < 1e-6 and ne > 1e-6:
+          err2 += ne
+        elif na >= 1e-6:
+          err2 += ne / na
+    S_rho, S_alp = v[1], np.array([v[3 + 2 * q] for q in range(4)])
+    for R in ranks:
+      R.cp ^= 1
+      R.cd ^= 1
+    if err1 < eps and err2 < eps:
+      reason = _lib.END_CONVERGED
+      break
+    if e1nan > 0 or v[15] > 0:
+      reason = _lib.END_NAN
+      break
+  iters = it + 1
+  return iters, reason, float(err1), float(err2), n_inner
+
+
+def gather_block(group):
+  """Assembles phi [2,nx,ny], rho [1,nx,ny], alp [4,1,nx,ny,2] of the block on the host (LocalGroup) / this rank's slab (DistGroup)."""
+  t = _dev.torch()
+  phi = t.cat([R.interior(R.phi[R.cp]) for R in group.ranks], dim=1).cpu().numpy()
+  rho = t.cat([R.interior(R.rho[R.cd]) for R in group.ranks], dim=1).cpu().numpy()
+  al = t.cat([R.interior(R.alp[R.cd]) for R in group.ranks], dim=2).cpu().numpy()        # [4,1,nx(l),ny] active components
+  alp = np.zeros(al.shape + (2,))
+  alp[:2, ..., 0] = al[:2]
+  alp[2:, ..., 1] = al[2:]
+  return phi, rho, alp

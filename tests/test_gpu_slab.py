@@ -1,0 +1,74 @@
+"""GPU: x-slab decomposition of one 2-D grid (BASELINE configs[4] building block, pdhg_b200/slab.py).
+
+P emulated ranks on ONE GPU (`LocalGroup`: the halo exchange, the two FFT transposes and the all-reduce are tensor copies)
+run the same per-phase kernels through `pdhg_ext_phase` that real ranks run between NCCL collectives; the result has to
+match the single-GPU solve of the same block: same stopping iteration, rel-Linf <= 1e-10 (the global error sums are
+accumulated in a different order, nothing else differs)."""
+import numpy as np
+import pytest
+
+from helpers import TOL, quiet, relmax
+
+pytestmark = pytest.mark.gpu
+
+
+def _single(rx, sf, nx, ny, epsl, T, stepsz, nmax):
+  n_ctrl, bc, _ = rx.problem_setup(1, 2)
+  x_arr = rx.make_x_arr(2, nx, ny, 2.0, 2.0)
+  fns, _ = quiet(sf.set_up_example_fns, 1, 2, 0)
+  info = {}
+  (res, errs), _ = quiet(rx.solve_HJ, 2, n_ctrl, 1, epsl, fns, nx, ny, 2, 2.0, 2.0, T, x_arr, 70.0, 2, stepsz, nmax, 10 ** 9, 1e-6, bc, info=info)
+  return fns, x_arr, res[0], info
+
+
+@pytest.mark.parametrize("P,nx,ny,epsl,nmax,stepsz", [(2, 32, 24, 0.0, 5000, 0.1), (4, 64, 32, 0.05, 300, 0.05), (3, 48, 16, 0.1, 60, 0.05),
+                                                        (1, 16, 16, 0.0, 40, 0.1)])
+def test_slab_decomposition_equals_single_gpu_solve(built_lib, P, nx, ny, epsl, nmax, stepsz):
+  from pdhg_b200 import run_example as rx, set_fns as sf, slab
+  from pdhg_b200.set_fns import set_up_J
+  T = 0.05
+  fns, x_arr, ref, info = _single(rx, sf, nx, ny, epsl, T, stepsz, nmax)
+  dt, dspatial = T / 1.0, (2.0 / nx, 2.0 / ny)
+  g = set_up_J(1, 2, (2.0, 2.0))(x_arr)[0]
+  ranks = [slab.SlabRank(r, P, fns, nx, ny, dt, dspatial, 70.0, x_arr) for r in range(P)]
+  grp = slab.LocalGroup(ranks)
+  slab.init_block(grp, g, 70.0)
+  iters, reason, err1, err2, n_inner = slab.solve_block_slab(grp, epsl, stepsz, nmax)
+  phi, rho, alp = slab.gather_block(grp)
+  assert [iters] == info["block_iters"], (iters, info["block_iters"])
+  _, phi_r, rho_r, alp_r = ref
+  assert relmax(phi, phi_r) < TOL
+  assert relmax(rho, rho_r) < TOL
+  assert relmax(alp, np.stack(alp_r)) < TOL
+
+
+def test_dist_group_world1_equals_local_group(built_lib):
+  """`DistGroup` (the torch.distributed / NCCL flavour) at world size 1 == `LocalGroup` at P = 1, bitwise."""
+  import os
+  import torch
+  import torch.distributed as dist
+  from pdhg_b200 import run_example as rx, set_fns as sf, slab
+  from pdhg_b200.set_fns import set_up_J
+  nx, ny, T = 32, 16, 0.05
+  x_arr = rx.make_x_arr(2, nx, ny, 2.0, 2.0)
+  fns, _ = quiet(sf.set_up_example_fns, 1, 2, 0)
+  g = set_up_J(1, 2, (2.0, 2.0))(x_arr)[0]
+  out = []
+  os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+  os.environ.setdefault("MASTER_PORT", "29541")
+  created = not dist.is_initialized()
+  if created:
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+  try:
+    for kind in ("local", "dist"):
+      R = slab.SlabRank(0, 1, fns, nx, ny, T, (2.0 / nx, 2.0 / ny), 70.0, x_arr)
+      grp = slab.LocalGroup([R]) if kind == "local" else slab.DistGroup(R, dist)
+      slab.init_block(grp, g, 70.0)
+      it = slab.solve_block_slab(grp, 0.0, 0.1, 30)
+      out.append((it, slab.gather_block(grp)))
+  finally:
+    if created:
+      dist.destroy_process_group()
+  assert out[0][0][:2] == out[1][0][:2]
+  for a, b in zip(out[0][1], out[1][1]):
+    assert np.array_equal(a, b)
