@@ -63,6 +63,7 @@ struct CoopArgs {
   double* ext_sums;          // MODE_PHASE: device array [kNQ] receiving the grid totals of phases D / E (may be null)
   int dbg_phase, dbg_pass;   // MODE_PHASE (profiling): phase id 0..3 = A,B,C,D and pass mask of phase B (bit 0,1,2)
   int d_pipe;         // 1: cp.async-pipelined dual sweep (ny even and the staging buffers fit shared memory)
+  int fast_y, fast_x; // warp-private 256-point transforms along y (phases A, C) / along x (phase B)
   double dxe, dye;
   const double* coef_xe;
   const double* coef_ye;
@@ -256,6 +257,121 @@ __device__ __forceinline__ double cont_point(int egno, bool last_k, double r00, 
   return res;
 }
 
+// residual of the VW-wide item at (k, i, j .. j+VW-1): loads + cont_point (shared by the tiled and the warp-private phase A)
+template <int ND, int VW, int EG>
+__device__ __forceinline__ Vec<VW> cont_item(const Ctx& c, const double* rho, const double* a1x, const double* a2x, const double* a1y,
+                                             const double* a2y, int k, int i, int j, double epsl, const Recip& rc, double c_dt) {
+  const CoopArgs& a = cargs();
+  const MarchParams& p = a.p;
+  const int K = p.K, nx = a.nxe, ny = a.nye;
+  const size_t n = (size_t)nx * ny;
+  constexpr int egno = EG;
+  Vec<VW> res;
+  const size_t o = (size_t)k * n + (size_t)i * ny;
+  const int jm = (j == 0) ? ny - 1 : j - 1, jq = (j + VW == ny) ? 0 : j + VW;
+  const Vec<VW> r00 = ldv<VW>(rho + o + j);
+  Vec<VW> rnext;
+  if (k + 1 < K) rnext = ldv<VW>(rho + o + n + j);
+  else {
+#pragma unroll
+    for (int e = 0; e < VW; ++e) rnext.e[e] = 0.0;
+  }
+  const double r_l = ldg1(rho + o + jm), r_r = ldg1(rho + o + jq);
+  Vec<VW> v1y, v2y;
+  double a1y_l = 0.0, a2y_r = 0.0;
+  if (egno != 3) {
+    v1y = ldv<VW>(a1y + o + j); v2y = ldv<VW>(a2y + o + j);
+    a1y_l = ldg1(a1y + o + jm); a2y_r = ldg1(a2y + o + jq);
+  } else {
+#pragma unroll
+    for (int e = 0; e < VW; ++e) { v1y.e[e] = 0.0; v2y.e[e] = 0.0; }
+  }
+  Vec<VW> rxm, rxp, v1x, v1xm, v2x, v2xp;
+  Nbr bx = nbr(i, nx, p.bc_x);
+  if (ND == 2) {
+    const size_t om = (size_t)k * n + (size_t)bx.m * ny, op = (size_t)k * n + (size_t)bx.p * ny;
+    rxm = ldv<VW>(rho + om + j); rxp = ldv<VW>(rho + op + j);
+    v1x = ldv<VW>(a1x + o + j); v1xm = ldv<VW>(a1x + om + j);
+    v2x = ldv<VW>(a2x + o + j); v2xp = ldv<VW>(a2x + op + j);
+  }
+  const double cx0 = (ND == 2 || egno == 3) ? c.cx()[i] : 0.0;
+  const double cxm = (ND == 2) ? c.cx()[bx.m] : 0.0, cxp = (ND == 2) ? c.cx()[bx.p] : 0.0;
+#pragma unroll
+  for (int e = 0; e < VW; ++e) {
+    const double rym = (e == 0) ? r_l : r00.e[0], ryp = (e == VW - 1) ? r_r : r00.e[VW - 1];
+    const double a1m = (e == 0) ? a1y_l : v1y.e[0], a2p = (e == VW - 1) ? a2y_r : v2y.e[VW - 1];
+    const int je = j + e;
+    const double cym = c.cy()[(e == 0) ? jm : j], cyp = c.cy()[(e == VW - 1) ? jq : j + VW - 1];
+    res.e[e] = cont_point<ND>(egno, k == K - 1, r00.e[e], rnext.e[e], rym, ryp, (ND == 2) ? rxm.e[e] : 0.0, (ND == 2) ? rxp.e[e] : 0.0,
+                              v1y.e[e], a1m, v2y.e[e], a2p, (ND == 2) ? v1x.e[e] : 0.0, (ND == 2) ? v1xm.e[e] : 0.0,
+                              (ND == 2) ? v2x.e[e] : 0.0, (ND == 2) ? v2xp.e[e] : 0.0, c.cy()[je], cym, cyp, cx0, cxm, cxp, bx.wm, bx.wp,
+                              epsl, rc, c_dt);
+  }
+  return res;
+}
+
+// residuals of the two x-adjacent double2 items (k, i, j..j+1) and (k, i+1, j..j+1), i even, of a 2-D grid, for a warp whose
+// lanes cover 64 consecutive columns (j = j0 + 2 lane): the x-neighbour rows are shared between the two items (16 vector loads
+// instead of 20, all issued before the arithmetic) and the y-neighbours come from the adjacent lanes by shuffle (only the two
+// edge lanes load a halo word).  Same operands as two cont_item calls => bitwise the same results.  All 32 lanes must call.
+template <int EG>
+__device__ __forceinline__ void cont_pair2d(const Ctx& c, const double* rho, const double* a1x, const double* a2x, const double* a1y,
+                                            const double* a2y, int k, int i, int j, int lane, double epsl, const Recip& rc, double c_dt,
+                                            Vec<2>& xa, Vec<2>& xb) {
+  const CoopArgs& a = cargs();
+  const MarchParams& p = a.p;
+  const int K = p.K, nx = a.nxe, ny = a.nye;
+  const size_t n = (size_t)nx * ny, base = (size_t)k * n;
+  constexpr int egno = EG;
+  const Nbr ba = nbr(i, nx, p.bc_x), bb = nbr(i + 1, nx, p.bc_x);
+  const size_t o_m = base + (size_t)ba.m * ny + j, o_a = base + (size_t)i * ny + j, o_b = o_a + ny, o_p = base + (size_t)bb.p * ny + j;
+  const Vec<2> R_m = ldv<2>(rho + o_m), R_a = ldv<2>(rho + o_a), R_b = ldv<2>(rho + o_b), R_p = ldv<2>(rho + o_p);
+  Vec<2> Rn_a, Rn_b;
+  if (k + 1 < K) { Rn_a = ldv<2>(rho + o_a + n); Rn_b = ldv<2>(rho + o_b + n); }
+  else { Rn_a.e[0] = Rn_a.e[1] = Rn_b.e[0] = Rn_b.e[1] = 0.0; }
+  const Vec<2> X1_m = ldv<2>(a1x + o_m), X1_a = ldv<2>(a1x + o_a), X1_b = ldv<2>(a1x + o_b);
+  const Vec<2> X2_a = ldv<2>(a2x + o_a), X2_b = ldv<2>(a2x + o_b), X2_p = ldv<2>(a2x + o_p);
+  Vec<2> Y1_a, Y1_b, Y2_a, Y2_b;
+  if (egno != 3) { Y1_a = ldv<2>(a1y + o_a); Y1_b = ldv<2>(a1y + o_b); Y2_a = ldv<2>(a2y + o_a); Y2_b = ldv<2>(a2y + o_b); }
+  else { Y1_a.e[0] = Y1_a.e[1] = Y1_b.e[0] = Y1_b.e[1] = Y2_a.e[0] = Y2_a.e[1] = Y2_b.e[0] = Y2_b.e[1] = 0.0; }
+  const int jm = (j == 0) ? ny - 1 : j - 1, jq = (j + 2 == ny) ? 0 : j + 2;
+  const size_t ra = base + (size_t)i * ny, rbo = ra + ny;
+  double rl_a = 0.0, rl_b = 0.0, rr_a = 0.0, rr_b = 0.0, y1l_a = 0.0, y1l_b = 0.0, y2r_a = 0.0, y2r_b = 0.0;
+  if (lane == 0) {
+    rl_a = ldg1(rho + ra + jm); rl_b = ldg1(rho + rbo + jm);
+    if (egno != 3) { y1l_a = ldg1(a1y + ra + jm); y1l_b = ldg1(a1y + rbo + jm); }
+  }
+  if (lane == 31) {
+    rr_a = ldg1(rho + ra + jq); rr_b = ldg1(rho + rbo + jq);
+    if (egno != 3) { y2r_a = ldg1(a2y + ra + jq); y2r_b = ldg1(a2y + rbo + jq); }
+  }
+  {
+    double t;
+    t = __shfl_up_sync(0xffffffffu, R_a.e[1], 1); if (lane != 0) rl_a = t;
+    t = __shfl_up_sync(0xffffffffu, R_b.e[1], 1); if (lane != 0) rl_b = t;
+    t = __shfl_down_sync(0xffffffffu, R_a.e[0], 1); if (lane != 31) rr_a = t;
+    t = __shfl_down_sync(0xffffffffu, R_b.e[0], 1); if (lane != 31) rr_b = t;
+    if (egno != 3) {
+      t = __shfl_up_sync(0xffffffffu, Y1_a.e[1], 1); if (lane != 0) y1l_a = t;
+      t = __shfl_up_sync(0xffffffffu, Y1_b.e[1], 1); if (lane != 0) y1l_b = t;
+      t = __shfl_down_sync(0xffffffffu, Y2_a.e[0], 1); if (lane != 31) y2r_a = t;
+      t = __shfl_down_sync(0xffffffffu, Y2_b.e[0], 1); if (lane != 31) y2r_b = t;
+    }
+  }
+  const double cx_a = c.cx()[i], cx_b = c.cx()[i + 1], cx_am = c.cx()[ba.m], cx_bp = c.cx()[bb.p];
+  const bool last = (k == K - 1);
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const double cy0 = c.cy()[j + e], cym = c.cy()[(e == 0) ? jm : j], cyp = c.cy()[(e == 1) ? jq : j + 1];
+    xa.e[e] = cont_point<2>(egno, last, R_a.e[e], Rn_a.e[e], (e == 0) ? rl_a : R_a.e[0], (e == 1) ? rr_a : R_a.e[1], R_m.e[e], R_b.e[e],
+                            Y1_a.e[e], (e == 0) ? y1l_a : Y1_a.e[0], Y2_a.e[e], (e == 1) ? y2r_a : Y2_a.e[1], X1_a.e[e], X1_m.e[e],
+                            X2_a.e[e], X2_b.e[e], cy0, cym, cyp, cx_a, cx_am, cx_b, ba.wm, ba.wp, epsl, rc, c_dt);
+    xb.e[e] = cont_point<2>(egno, last, R_b.e[e], Rn_b.e[e], (e == 0) ? rl_b : R_b.e[0], (e == 1) ? rr_b : R_b.e[1], R_a.e[e], R_p.e[e],
+                            Y1_b.e[e], (e == 0) ? y1l_b : Y1_b.e[0], Y2_b.e[e], (e == 1) ? y2r_b : Y2_b.e[1], X1_b.e[e], X1_a.e[e],
+                            X2_b.e[e], X2_p.e[e], cy0, cym, cyp, cx_b, cx_a, cx_bp, bb.wm, bb.wp, epsl, rc, c_dt);
+  }
+}
+
 // ---- phase A: residual rows -> y-FFT -> transposed half spectrum ----
 template <int ND, int VW, int EG>
 __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
@@ -275,7 +391,6 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
   const double* a1y = al + (size_t)(2 * ND - 2) * KN;
   const double* a2y = al + (size_t)(2 * ND - 1) * KN;
   const int tid = threadIdx.x, nth = blockDim.x;
-  constexpr int egno = EG;
   const Recip rc(p.dt, a.dxe, a.dye, 1.0);
   const double c_dt = p.c_on_rho * rc.idt;
   const int ny2 = ny / VW;
@@ -291,46 +406,7 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
       for (int e = 0; e < VW; ++e) res.e[e] = 0.0;
       if (lr < nrows) {
         const int r = r0 + lr, k = fast_div_exact(r, nx, c.inv_nx), i = r - k * nx;
-        const size_t o = (size_t)k * n + (size_t)i * ny;
-        const int jm = (j == 0) ? ny - 1 : j - 1, jq = (j + VW == ny) ? 0 : j + VW;
-        const Vec<VW> r00 = ldv<VW>(rho + o + j);
-        Vec<VW> rnext;
-        if (k + 1 < K) rnext = ldv<VW>(rho + o + n + j);
-        else {
-#pragma unroll
-          for (int e = 0; e < VW; ++e) rnext.e[e] = 0.0;
-        }
-        const double r_l = ldg1(rho + o + jm), r_r = ldg1(rho + o + jq);
-        Vec<VW> v1y, v2y;
-        double a1y_l = 0.0, a2y_r = 0.0;
-        if (egno != 3) {
-          v1y = ldv<VW>(a1y + o + j); v2y = ldv<VW>(a2y + o + j);
-          a1y_l = ldg1(a1y + o + jm); a2y_r = ldg1(a2y + o + jq);
-        } else {
-#pragma unroll
-          for (int e = 0; e < VW; ++e) { v1y.e[e] = 0.0; v2y.e[e] = 0.0; }
-        }
-        Vec<VW> rxm, rxp, v1x, v1xm, v2x, v2xp;
-        Nbr bx = nbr(i, nx, p.bc_x);
-        if (ND == 2) {
-          const size_t om = (size_t)k * n + (size_t)bx.m * ny, op = (size_t)k * n + (size_t)bx.p * ny;
-          rxm = ldv<VW>(rho + om + j); rxp = ldv<VW>(rho + op + j);
-          v1x = ldv<VW>(a1x + o + j); v1xm = ldv<VW>(a1x + om + j);
-          v2x = ldv<VW>(a2x + o + j); v2xp = ldv<VW>(a2x + op + j);
-        }
-        const double cx0 = (ND == 2 || egno == 3) ? c.cx()[i] : 0.0;
-        const double cxm = (ND == 2) ? c.cx()[bx.m] : 0.0, cxp = (ND == 2) ? c.cx()[bx.p] : 0.0;
-#pragma unroll
-        for (int e = 0; e < VW; ++e) {
-          const double rym = (e == 0) ? r_l : r00.e[0], ryp = (e == VW - 1) ? r_r : r00.e[VW - 1];
-          const double a1m = (e == 0) ? a1y_l : v1y.e[0], a2p = (e == VW - 1) ? a2y_r : v2y.e[VW - 1];
-          const int je = j + e;
-          const double cym = c.cy()[(e == 0) ? jm : j], cyp = c.cy()[(e == VW - 1) ? jq : j + VW - 1];
-          res.e[e] = cont_point<ND>(egno, k == K - 1, r00.e[e], rnext.e[e], rym, ryp, (ND == 2) ? rxm.e[e] : 0.0, (ND == 2) ? rxp.e[e] : 0.0,
-                                    v1y.e[e], a1m, v2y.e[e], a2p, (ND == 2) ? v1x.e[e] : 0.0, (ND == 2) ? v1xm.e[e] : 0.0,
-                                    (ND == 2) ? v2x.e[e] : 0.0, (ND == 2) ? v2xp.e[e] : 0.0, c.cy()[je], cym, cyp, cx0, cxm, cxp, bx.wm, bx.wp,
-                                    epsl, rc, c_dt);
-        }
+        res = cont_item<ND, VW, EG>(c, rho, a1x, a2x, a1y, a2y, k, i, j, epsl, rc, c_dt);
       }
       double* dst = reinterpret_cast<double*>(&buf0[(size_t)(lr >> 1) * ld + fpad(j)]) + (lr & 1);
 #pragma unroll
@@ -359,6 +435,241 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
   }
 }
 
+// ===================================================================================================================
+// Warp-private fast path for 256-point transforms (the BASELINE 2-D grid): 256 = 16 x 16, every lane holds 16 complex
+// elements of one row in registers, the only exchange is a 16 x 16 transpose through the warp's own two-row shared-memory
+// buffer, and the only synchronisation is __syncwarp().  No block barrier anywhere in phases A / B / C, so the 16 warps of
+// an SM run decoupled (loads of some overlap the butterflies of others) and global memory <-> registers moves are direct:
+// 16 (B) or 32 (C) independent 16-byte loads per lane in flight.
+//   lane = 16 p + jj: complex row p of the warp's pair, elements jj + 16 t.   in: v[t] = x[jj + 16 t]   out: v[q] = X[jj + 16 q]
+// ===================================================================================================================
+constexpr int kW256Ld = 273;      // fft_ld(256): padded row stride (complex elements)
+
+template <bool INV>
+__device__ __forceinline__ void wfft256_first(double2 (&v)[16], double2* rb, int jj) {
+  Dft<16, INV>::run(v);                                       // Stockham stage 1 (Ns = 1): outputs q -> element 16 jj + q
+  __syncwarp();                                               // earlier reads of the buffer by other lanes are done
+#pragma unroll
+  for (int q = 0; q < 16; ++q) rb[17 * jj + q] = v[q];        // fpad(16 jj + q)
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < 16; ++t) v[t] = rb[jj + 17 * t];        // fpad(jj + 16 t)
+}
+template <bool INV>
+__device__ __forceinline__ void wfft256_second(double2 (&v)[16], int jj, const double2* tw) {
+  // stage 2 (Ns = 16): twiddles W256^(t jj); table loads for t = 1..3 and 4, 8, 12, products for the rest
+  double2 wb[4];
+  wb[0] = make_double2(1.0, 0.0);
+#pragma unroll
+  for (int t = 1; t < 4; ++t) { wb[t] = tw[t * jj]; if (INV) wb[t].y = -wb[t].y; }
+#pragma unroll
+  for (int t = 1; t < 4; ++t) v[t] = cmul(v[t], wb[t]);
+#pragma unroll
+  for (int a4 = 1; a4 < 4; ++a4) {
+    double2 wa = tw[4 * a4 * jj];
+    if (INV) wa.y = -wa.y;
+    v[4 * a4] = cmul(v[4 * a4], wa);
+#pragma unroll
+    for (int t = 1; t < 4; ++t) v[4 * a4 + t] = cmul(v[4 * a4 + t], cmul(wa, wb[t]));
+  }
+  Dft<16, INV>::run(v);                                       // outputs q -> element jj + 16 q
+}
+template <bool INV>
+__device__ __forceinline__ void wfft256(double2 (&v)[16], double2* rb, int jj, const double2* tw) {
+  wfft256_first<INV>(v, rb, jj);
+  wfft256_second<INV>(v, jj, tw);
+}
+
+// phase A, ny == 256: a warp takes 4 consecutive residual rows (= 2 complex rows), computes them with the coalesced
+// double2 pattern into its buffer, transforms, splits the two real spectra with lane shuffles (X[m] and X[256 - m] sit
+// in lanes jj and 16 - jj) and stores the half spectrum transposed.
+template <int ND, int EG>
+__device__ __noinline__ void phase_A_w256(Ctx& c, int cd, double epsl) {
+  const CoopArgs& a = cargs();
+  const MarchParams& p = a.p;
+  const int K = p.K, nx = a.nxe, nyh = a.nyh;
+  constexpr int ny = 256;
+  const size_t KN = (size_t)K * nx * ny;
+  const int rows = K * nx, nunits = (rows + 3) >> 2;
+  const double* rho = as_global(a.w.rho[cd]);
+  const double* al = as_global(a.w.alp[cd]);
+  double2* ztg = as_global(a.w.zt);
+  const double* a1x = al;
+  const double* a2x = al + KN;
+  const double* a1y = al + (size_t)(2 * ND - 2) * KN;
+  const double* a2y = al + (size_t)(2 * ND - 1) * KN;
+  const Recip rc(p.dt, a.dxe, a.dye, 1.0);
+  const double c_dt = p.c_on_rho * rc.idt;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pr = lane >> 4, jj = lane & 15;
+  double2* wbuf = c.work() + (size_t)warp * 2 * kW256Ld;
+  double2* rb = wbuf + pr * kW256Ld;
+  const int src = (lane & 16) | ((16 - jj) & 15);
+  const int nwt = gridDim.x * kWarps;
+  const bool paired = (ND == 2) && ((nx & 1) == 0);     // rows 2p, 2p+1 of a unit are x-neighbours in the same time row
+  for (int u = warp * gridDim.x + blockIdx.x; u < nunits; u += nwt) {
+    const int r0 = 4 * u;
+    __syncwarp();
+#pragma unroll 1
+    for (int pp = 0; pp < 2; ++pp) {
+      const int ra = r0 + 2 * pp, rbw = ra + 1;
+      const bool va = ra < rows, vb = rbw < rows;
+      const int ka = fast_div_exact(va ? ra : 0, nx, c.inv_nx), ia = (va ? ra : 0) - ka * nx;
+      const int kb = fast_div_exact(vb ? rbw : 0, nx, c.inv_nx), ib = (vb ? rbw : 0) - kb * nx;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        const int j = 2 * lane + 64 * cc;
+        Vec<2> xa, xb;
+        xa.e[0] = xa.e[1] = xb.e[0] = xb.e[1] = 0.0;
+        if (ND == 2 && paired) {
+          if (va) cont_pair2d<EG>(c, rho, a1x, a2x, a1y, a2y, ka, ia, j, lane, epsl, rc, c_dt, xa, xb);     // (va == vb, warp-uniform)
+        } else {
+          if (va) xa = cont_item<ND, 2, EG>(c, rho, a1x, a2x, a1y, a2y, ka, ia, j, epsl, rc, c_dt);
+          if (vb) xb = cont_item<ND, 2, EG>(c, rho, a1x, a2x, a1y, a2y, kb, ib, j, epsl, rc, c_dt);
+        }
+        double2* d = wbuf + pp * kW256Ld + fpad(j);
+        d[0] = make_double2(xa.e[0], xb.e[0]);
+        d[1] = make_double2(xa.e[1], xb.e[1]);
+      }
+    }
+    __syncwarp();
+    double2 v[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) v[t] = rb[jj + 17 * t];
+    wfft256<false>(v, rb, jj, c.twy());
+    // split: Z_a[m] = (X[m] + conj X[N-m]) / 2, Z_b[m] = (X[m] - conj X[N-m]) / (2i), m = jj + 16 q <= 128
+    const int ra = r0 + 2 * pr, rbw = ra + 1;
+    const bool va = ra < rows, vb = rbw < rows;
+    const int ka = fast_div_exact(va ? ra : 0, nx, c.inv_nx), ia = (va ? ra : 0) - ka * nx;
+    const int kb = fast_div_exact(vb ? rbw : 0, nx, c.inv_nx), ib = (vb ? rbw : 0) - kb * nx;
+    double2* za = ztg + (size_t)ka * nyh * nx + ia;
+    double2* zb = ztg + (size_t)kb * nyh * nx + ib;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const double2 mine = (jj == 0) ? v[(16 - q) & 15] : v[15 - q];
+      double2 z2;
+      z2.x = __shfl_sync(0xffffffffu, mine.x, src);
+      z2.y = __shfl_sync(0xffffffffu, mine.y, src);
+      const double2 z1 = v[q];
+      const size_t mo = (size_t)(jj + 16 * q) * nx;
+      if (va) stg2(za + mo, make_double2(0.5 * (z1.x + z2.x), 0.5 * (z1.y - z2.y)));
+      if (vb) stg2(zb + mo, make_double2(0.5 * (z1.y + z2.y), 0.5 * (z2.x - z1.x)));
+    }
+    if (jj == 0) {                       // m = 128 is its own mirror
+      const double2 z1 = v[8];
+      const size_t mo = (size_t)128 * nx;
+      if (va) stg2(za + mo, make_double2(z1.x, 0.0));
+      if (vb) stg2(zb + mo, make_double2(z1.y, 0.0));
+    }
+  }
+}
+
+// phase B, nx == 256 (periodic): x-transforms of two (k, ky) rows per warp, global <-> registers.
+//   DIR = +1 forward only (pass 1 of a coupled solve), -1 inverse only (pass 3), 0 forward + per-mode scaling + inverse
+template <int DIR>
+__device__ __noinline__ void phase_B_w256(Ctx& c, double2* zt, int nrows) {
+  const CoopArgs& a = cargs();
+  const MarchParams& p = a.p;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pr = lane >> 4, jj = lane & 15;
+  double2* rb = c.work() + (size_t)(warp * 2 + pr) * kW256Ld;
+  const int npairs = (nrows + 1) >> 1, nwt = gridDim.x * kWarps;
+  const double ctk = (p.K == 1) ? p.Ct_over_dt2 : 0.0;
+  for (int u = warp * gridDim.x + blockIdx.x; u < npairs; u += nwt) {
+    const int row = 2 * u + pr;
+    const bool valid = row < nrows;
+    double2* g = zt + (size_t)(valid ? row : 0) * 256 + jj;
+    double2 v[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) v[t] = valid ? ldg2(g + 16 * t) : make_double2(0.0, 0.0);
+    if (DIR >= 0) wfft256<false>(v, rb, jj, c.twx());
+    if (DIR == 0) {
+      const int ky = row - (row / a.nyh) * a.nyh;
+      const double* dg = p.diag + a.ky_off + (valid ? ky : 0);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const double rd = 1.0 / (ldg1(dg + (size_t)(jj + 16 * q) * a.nyh_tab) + ctk);
+        v[q].x *= rd; v[q].y *= rd;
+      }
+    }
+    if (DIR <= 0) wfft256<true>(v, rb, jj, c.twx());
+    if (valid) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) stg2(g + 16 * q, v[q]);
+    }
+  }
+}
+
+// phase C, ny == 256: rebuilds the full spectrum of the complex row (u_a + i u_b) from the two half spectra straight from
+// global memory, inverse transform, phi update on the lane's 16 (strided) columns of both rows.
+__device__ __noinline__ void phase_C_w256(Ctx& c, const double* phi_prev, double* phi_next, double* phib, double tau) {
+  const CoopArgs& a = cargs();
+  const MarchParams& p = a.p;
+  const int K = p.K, nx = a.nxe, nyh = a.nyh;
+  constexpr int ny = 256;
+  const size_t n = (size_t)nx * ny;
+  const int rows = K * nx, nunits = (rows + 3) >> 2;
+  const double inv_nn = 1.0 / ((double)nx * (double)ny);
+  const double2* ztg = as_global(a.w.zt);
+  phi_prev = as_global(phi_prev); phi_next = as_global(phi_next);
+  if (phib) phib = as_global(phib);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pr = lane >> 4, jj = lane & 15;
+  double2* rb = c.work() + (size_t)(warp * 2 + pr) * kW256Ld;
+  const int nwt = gridDim.x * kWarps;
+  double s_d = 0.0, s_p = 0.0, s_n = 0.0;
+  for (int u = warp * gridDim.x + blockIdx.x; u < nunits; u += nwt) {
+    const int ra = 4 * u + 2 * pr, rbw = ra + 1;
+    const bool va = ra < rows, vb = rbw < rows;
+    const int ka = fast_div_exact(va ? ra : 0, nx, c.inv_nx), ia = (va ? ra : 0) - ka * nx;
+    const int kb = fast_div_exact(vb ? rbw : 0, nx, c.inv_nx), ib = (vb ? rbw : 0) - kb * nx;
+    const double2* za = ztg + (size_t)ka * nyh * nx + ia;
+    const double2* zb = ztg + (size_t)kb * nyh * nx + ib;
+    double2 v[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const bool lo = (t < 8) || (t == 8 && jj == 0);
+      const int m = jj + 16 * t, mm = lo ? m : 256 - m;
+      const double2 ua = va ? ldg2(za + (size_t)mm * nx) : make_double2(0.0, 0.0);
+      const double2 ub = vb ? ldg2(zb + (size_t)mm * nx) : make_double2(0.0, 0.0);
+      v[t] = lo ? make_double2(ua.x - ub.y, ua.y + ub.x) : make_double2(ua.x + ub.y, ub.x - ua.y);
+    }
+    wfft256_first<true>(v, rb, jj);
+    // phi_prev of row a is requested before the second butterfly pass, that of row b before row a's update: the latency of
+    // both hides behind arithmetic (the loads are volatile asm, so they stay where they are written)
+    const size_t ga = (size_t)(ka + 1) * n + (size_t)ia * ny + jj, gb = (size_t)(kb + 1) * n + (size_t)ib * ny + jj;
+    double pa[16], pb[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) pa[q] = va ? ldg1(phi_prev + ga + 16 * q) : 0.0;
+    wfft256_second<true>(v, jj, c.twy());
+    if (va) {
+      const bool acc = (ia >= a.sum_lo && ia < a.sum_hi);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const double pp = pa[q];
+        const double pn = pp + tau * (v[q].x * inv_nn);
+        const double df = pn - pp;
+        if (acc) { s_d += df * df; s_p += pp * pp; s_n += is_nan(pn) ? 1.0 : 0.0; }
+        stg1(phi_next + ga + 16 * q, pn);
+        if (phib) stg1(phib + ga + 16 * q, 2 * pn - pp);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) pb[q] = vb ? ldg1(phi_prev + gb + 16 * q) : 0.0;
+    if (vb) {
+      const bool acc = (ib >= a.sum_lo && ib < a.sum_hi);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const double pp = pb[q];
+        const double pn = pp + tau * (v[q].y * inv_nn);
+        const double df = pn - pp;
+        if (acc) { s_d += df * df; s_p += pp * pp; s_n += is_nan(pn) ? 1.0 : 0.0; }
+        stg1(phi_next + gb + 16 * q, pn);
+        if (phib) stg1(phib + gb + 16 * q, 2 * pn - pp);
+      }
+    }
+  }
+  const double sums[3] = {s_d, s_p, s_n};
+  cta_partials<3>(c, sums, 16);
+}
+
 // Thomas recurrences over k for one real component of one Fourier mode (item w of a [K][2*modes] real array)
 __device__ __forceinline__ void thomas_component(double* ztd, const double* den, const double* tu, int K, size_t modes2, size_t w,
                                                  double ct2) {
@@ -366,7 +677,14 @@ __device__ __forceinline__ void thomas_component(double* ztd, const double* den,
   ztd = as_global(ztd); den = as_global(den); tu = as_global(tu);
   double bp = 0.0;
   int k = 0;
-  for (; k + 4 <= K; k += 4) {      // 4 independent loads ahead of the dependent chain
+  for (; k + 8 <= K; k += 8) {      // 16 independent loads ahead of the dependent chain
+    double v[8], dn[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { v[q] = ldg1(ztd + (size_t)(k + q) * modes2 + w); dn[q] = ldg1(den + (size_t)(k + q) * modes + m); }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { bp = (v[q] + ct2 * bp) * dn[q]; stg1(ztd + (size_t)(k + q) * modes2 + w, bp); }
+  }
+  for (; k + 4 <= K; k += 4) {
     double v[4], dn[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) { v[q] = ldg1(ztd + (size_t)(k + q) * modes2 + w); dn[q] = ldg1(den + (size_t)(k + q) * modes + m); }
@@ -379,6 +697,13 @@ __device__ __forceinline__ void thomas_component(double* ztd, const double* den,
   }
   double xs = bp;
   k = K - 2;
+  for (; k - 7 >= 0; k -= 8) {
+    double v[8], tv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { v[q] = ldg1(ztd + (size_t)(k - q) * modes2 + w); tv[q] = ldg1(tu + (size_t)(k - q) * modes + m); }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { xs = v[q] - tv[q] * xs; stg1(ztd + (size_t)(k - q) * modes2 + w, xs); }
+  }
   for (; k - 3 >= 0; k -= 4) {
     double v[4], tv[4];
 #pragma unroll
@@ -424,6 +749,18 @@ __device__ __noinline__ void phase_B(Ctx& c) {
   const int ntile = (nyh + TKY - 1) / TKY;
   const int nunits = K * ntile;
   const int pmask = (a.mode == MODE_PHASE) ? a.dbg_pass : 7;
+  if (a.fast_x) {
+    if (!coupled) { if (pmask & 1) phase_B_w256<0>(c, zt, K * nyh); return; }
+    if (pmask & 1) phase_B_w256<1>(c, zt, K * nyh);
+    c.grid.sync();
+    c.tick(3);
+    for (size_t w = (size_t)blockIdx.x * nth + tid; w < ((pmask & 2) ? 2 * modes : 0); w += (size_t)gridDim.x * nth)
+      thomas_component(reinterpret_cast<double*>(zt), a.w.den, a.w.tu, K, 2 * modes, w, ct2);
+    c.grid.sync();
+    c.tick(4);
+    if (pmask & 4) phase_B_w256<-1>(c, zt, K * nyh);
+    return;
+  }
   // pass 1: x-FFT of every (k, ky) row; uncoupled modes are solved and transformed back in the same pass
   for (int u = blockIdx.x; u < ((pmask & 1) ? nunits : 0); u += gridDim.x) {
     const int k = u / ntile, ky0 = (u - k * ntile) * TKY;
@@ -889,6 +1226,7 @@ __device__ __noinline__ void phase_E(Ctx& c, const double* rho_n, const double* 
 template <int EG>
 __device__ __forceinline__ void run_A_eg(Ctx& c, int cd, double epsl) {
   const bool v2 = (cargs().nye & 1) == 0;
+  if (cargs().fast_y) { if (cargs().has_x) phase_A_w256<2, EG>(c, cd, epsl); else phase_A_w256<1, EG>(c, cd, epsl); return; }
   if (cargs().has_x) { if (v2) phase_A<2, 2, EG>(c, cd, epsl); else phase_A<2, 1, EG>(c, cd, epsl); }
   else { if (v2) phase_A<1, 2, EG>(c, cd, epsl); else phase_A<1, 1, EG>(c, cd, epsl); }
 }
@@ -897,6 +1235,7 @@ __device__ __forceinline__ void run_A(Ctx& c, int cd, double epsl) {
   if (cargs().p.egno == 3) run_A_eg<3>(c, cd, epsl); else run_A_eg<1>(c, cd, epsl);
 }
 __device__ __forceinline__ void run_C(Ctx& c, const double* pp, double* pn, double* pb, double tau) {
+  if (cargs().fast_y) { phase_C_w256(c, pp, pn, pb, tau); return; }
   if ((cargs().nye & 1) == 0) phase_C<2>(c, pp, pn, pb, tau); else phase_C<1>(c, pp, pn, pb, tau);
 }
 template <int EG>
@@ -1231,7 +1570,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
 // ------------------------------------------- host side -------------------------------------------
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-struct CoopGeom { int nxe, nye, nyh, TR, TKY, grid, d_pipe; size_t smem; };
+struct CoopGeom { int nxe, nye, nyh, TR, TKY, grid, d_pipe, fast_y, fast_x; size_t smem; };
 
 static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   CoopGeom g;
@@ -1255,6 +1594,15 @@ static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   const size_t smD = (size_t)kWarps * 2 * ((p.ndim == 2) ? DStage<2>::kBytes : DStage<1>::kBytes);
   g.d_pipe = ((g.nye & 1) == 0 && smD <= cap && getenv("PDHG_DPIPE") != nullptr) ? 1 : 0;   // opt-in: measured slower (L1 shrinks)
   if (g.d_pipe && smD > work) work = smD;
+  // warp-private 256-point transforms: two padded rows per warp
+  const size_t smW = (size_t)kWarps * 2 * kW256Ld * 16;
+  const bool w256 = getenv("PDHG_NO_W256") == nullptr && smW <= cap;
+  // (a unit is one warp's work; below ~8 units per SM the tiled path, which spreads one tile over a whole CTA, is faster)
+  const bool force = getenv("PDHG_FORCE_W256") != nullptr;
+  const bool many_y = force || (rows + 3) / 4 >= 8 * sm_count, many_x = force || (p.K * g.nyh + 1) / 2 >= 8 * sm_count;
+  g.fast_y = (w256 && many_y && g.nye == 256 && (p.ndim == 1 ? p.bc_x == 0 : p.bc_y == 0)) ? 1 : 0;
+  g.fast_x = (w256 && many_x && g.nxe == 256 && p.ndim == 2 && p.bc_x == 0) ? 1 : 0;
+  if ((g.fast_y || g.fast_x) && smW > work) work = smW;
   g.smem = tab + work;
   g.grid = sm_count * kCtasPerSm;
   return g;
@@ -1318,7 +1666,7 @@ static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, 
   a.p = p;
   a.w = carve(p, ws);
   a.b = b; a.mode = mode; a.A = 2 * p.ndim;
-  a.nxe = g.nxe; a.nye = g.nye; a.nyh = g.nyh; a.TR = g.TR; a.TKY = g.TKY; a.d_pipe = g.d_pipe;
+  a.nxe = g.nxe; a.nye = g.nye; a.nyh = g.nyh; a.TR = g.TR; a.TKY = g.TKY; a.d_pipe = g.d_pipe; a.fast_y = g.fast_y; a.fast_x = g.fast_x;
   a.has_x = (p.ndim == 2);
   if (p.ndim == 1) {
     a.dxe = 1.0; a.dye = p.dx; a.coef_xe = p.coef_x; a.coef_ye = p.coef_x; a.tw_xe = p.tw_x; a.tw_ye = p.tw_x;

@@ -189,6 +189,39 @@ def test_cfg3_grid_first_iterations_vs_oracle(pk):
   assert relmax(errs[0], errs_o[0]) < 1e-7 and info["block_iters"] == [25]
 
 
+@pytest.mark.parametrize("ndim,nx,ny,nt,epsl,nmax", [(2, 256, 256, 4, 0.002, 6), (2, 64, 256, 3, 0.0, 8), (2, 256, 48, 3, 0.005, 8), (1, 256, 1, 4, 0.003, 40),
+                                                       (1, 256, 1, 6, 0.0, 30)])
+def test_warp_private_256_point_transforms_vs_oracle(pk, ndim, nx, ny, nt, epsl, nmax):
+  """The barrier-free 256-point fast path of the cooperative kernel (phases A/C when ny == 256, phase B when nx == 256; 1-D
+  grids run with their x axis as the contiguous axis) on coupled space-time blocks (K = nt - 1 > 1, Thomas in t), including
+  row counts that leave the last 4-row unit partly empty, against the oracle; and == the generic tiled path (PDHG_NO_W256)."""
+  from oracle import pdhg_numpy as orc
+  rx = pk["rx"]
+  n_ctrl, bc, _ = rx.problem_setup(1, ndim)
+  x_arr = rx.make_x_arr(ndim, nx, ny, 2.0, 2.0)
+  fns, _ = quiet(pk["sf"].set_up_example_fns, 1, ndim, 0)
+  out = []
+  T = (nt - 1) / 64.0
+  os.environ["PDHG_FORCE_PATH"] = "2"
+  try:
+    for env in ("PDHG_FORCE_W256", "PDHG_NO_W256"):     # (by default the fast path is only taken when there are >= 8 units per SM)
+      os.environ[env] = "1"
+      (res, errs), _ = quiet(rx.solve_HJ, ndim, n_ctrl, 1, epsl, fns, nx, ny, nt, 2.0, 2.0, T, x_arr, 70.0, nt, 0.1, nmax, 10, 1e-6, bc)
+      os.environ.pop(env)
+      out.append((res, errs))
+  finally:
+    for env in ("PDHG_FORCE_PATH", "PDHG_FORCE_W256", "PDHG_NO_W256"):
+      os.environ.pop(env, None)
+  res_o, errs_o = orc.solve_HJ(ndim, n_ctrl, 1, epsl, orc.set_up_example_fns(1, ndim, 0), nx, ny, nt, 2.0, 2.0, T, x_arr, 70.0, nt, 0.1, nmax, 10,
+                               1e-6, bc)
+  for res, errs in out:
+    for a, b in zip(res[0][1:], res_o[0][1:]):
+      assert relmax(a, b) < TOL
+    assert relmax(errs[0], errs_o[0]) < 1e-7
+  for a, b in zip(out[0][0][0][1:], out[1][0][0][1:]):
+    assert relmax(a, b) < 1e-12
+
+
 def test_spacetime_block_2d_vs_oracle(pk):
   """time_step_per_PDHG = nt (one space-time block, the HBM-bound regime): FFT-xy + Thomas-t over K = 8 rows."""
   from oracle import pdhg_numpy as orc
