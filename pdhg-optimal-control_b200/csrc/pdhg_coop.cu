@@ -64,6 +64,7 @@ struct CoopArgs {
   int dbg_phase, dbg_pass;   // MODE_PHASE (profiling): phase id 0..3 = A,B,C,D and pass mask of phase B (bit 0,1,2)
   int d_pipe;         // 1: cp.async-pipelined dual sweep (ny even and the staging buffers fit shared memory)
   int fast_y, fast_x; // warp-private 256-point transforms along y (phases A, C) / along x (phase B)
+  int pf_l2;          // bulk L2 prefetch of a unit's input rows (opt-in PDHG_PF=1: measured slower)
   double dxe, dye;
   const double* coef_xe;
   const double* coef_ye;
@@ -162,6 +163,10 @@ __device__ __forceinline__ void stg1(double* p, double v) {
 }
 __device__ __forceinline__ void stg2(void* p, double2 v) {
   asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(p)), "d"(v.x), "d"(v.y) : "memory");
+}
+// one instruction (warp-uniform operands) asks L2 to fetch `bytes` (multiple of 16) starting at the 16-byte aligned p
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(bytes) : "memory");
 }
 template <int VW> __device__ __forceinline__ Vec<VW> ldv(const double* p) {
   Vec<VW> r;
@@ -314,36 +319,49 @@ __device__ __forceinline__ Vec<VW> cont_item(const Ctx& c, const double* rho, co
 // lanes cover 64 consecutive columns (j = j0 + 2 lane): the x-neighbour rows are shared between the two items (16 vector loads
 // instead of 20, all issued before the arithmetic) and the y-neighbours come from the adjacent lanes by shuffle (only the two
 // edge lanes load a halo word).  Same operands as two cont_item calls => bitwise the same results.  All 32 lanes must call.
-template <int EG>
+struct PairRows {             // per row pair (k, i), (k, i+1): what does not depend on the column (32-bit element offsets: K n < 2^31)
+  unsigned o_m, o_a, o_p;     // rows i-1, i, i+2 of time row k   (row i+1 = o_a + ny; next time row = + n)
+  int i;
+  bool last;
+};
+__device__ __forceinline__ PairRows pair_rows(int k, int i) {
+  const CoopArgs& a = cargs();
+  const int nx = a.nxe, ny = a.nye;
+  const unsigned base = (unsigned)k * (unsigned)(nx * ny);
+  const Nbr ba = nbr(i, nx, a.p.bc_x), bb = nbr(i + 1, nx, a.p.bc_x);
+  PairRows r;
+  r.o_m = base + (unsigned)(ba.m * ny); r.o_a = base + (unsigned)(i * ny); r.o_p = base + (unsigned)(bb.p * ny);
+  r.i = i;
+  r.last = (k == a.p.K - 1);
+  return r;
+}
+template <int EG, bool MATH = true>
 __device__ __forceinline__ void cont_pair2d(const Ctx& c, const double* rho, const double* a1x, const double* a2x, const double* a1y,
-                                            const double* a2y, int k, int i, int j, int lane, double epsl, const Recip& rc, double c_dt,
+                                            const double* a2y, const PairRows& q, int j, int lane, double epsl, const Recip& rc, double c_dt,
                                             Vec<2>& xa, Vec<2>& xb) {
   const CoopArgs& a = cargs();
-  const MarchParams& p = a.p;
-  const int K = p.K, nx = a.nxe, ny = a.nye;
-  const size_t n = (size_t)nx * ny, base = (size_t)k * n;
+  const int nx = a.nxe, ny = a.nye;
+  const unsigned n = (unsigned)(nx * ny);
   constexpr int egno = EG;
-  const Nbr ba = nbr(i, nx, p.bc_x), bb = nbr(i + 1, nx, p.bc_x);
-  const size_t o_m = base + (size_t)ba.m * ny + j, o_a = base + (size_t)i * ny + j, o_b = o_a + ny, o_p = base + (size_t)bb.p * ny + j;
-  const Vec<2> R_m = ldv<2>(rho + o_m), R_a = ldv<2>(rho + o_a), R_b = ldv<2>(rho + o_b), R_p = ldv<2>(rho + o_p);
+  const unsigned jm_ = q.o_m + j, ja_ = q.o_a + j, jb_ = ja_ + ny, jp_ = q.o_p + j;
+  const Vec<2> R_m = ldv<2>(rho + jm_), R_a = ldv<2>(rho + ja_), R_b = ldv<2>(rho + jb_), R_p = ldv<2>(rho + jp_);
   Vec<2> Rn_a, Rn_b;
-  if (k + 1 < K) { Rn_a = ldv<2>(rho + o_a + n); Rn_b = ldv<2>(rho + o_b + n); }
+  if (!q.last) { Rn_a = ldv<2>(rho + (ja_ + n)); Rn_b = ldv<2>(rho + (jb_ + n)); }
   else { Rn_a.e[0] = Rn_a.e[1] = Rn_b.e[0] = Rn_b.e[1] = 0.0; }
-  const Vec<2> X1_m = ldv<2>(a1x + o_m), X1_a = ldv<2>(a1x + o_a), X1_b = ldv<2>(a1x + o_b);
-  const Vec<2> X2_a = ldv<2>(a2x + o_a), X2_b = ldv<2>(a2x + o_b), X2_p = ldv<2>(a2x + o_p);
+  const Vec<2> X1_m = ldv<2>(a1x + jm_), X1_a = ldv<2>(a1x + ja_), X1_b = ldv<2>(a1x + jb_);
+  const Vec<2> X2_a = ldv<2>(a2x + ja_), X2_b = ldv<2>(a2x + jb_), X2_p = ldv<2>(a2x + jp_);
   Vec<2> Y1_a, Y1_b, Y2_a, Y2_b;
-  if (egno != 3) { Y1_a = ldv<2>(a1y + o_a); Y1_b = ldv<2>(a1y + o_b); Y2_a = ldv<2>(a2y + o_a); Y2_b = ldv<2>(a2y + o_b); }
+  if (egno != 3) { Y1_a = ldv<2>(a1y + ja_); Y1_b = ldv<2>(a1y + jb_); Y2_a = ldv<2>(a2y + ja_); Y2_b = ldv<2>(a2y + jb_); }
   else { Y1_a.e[0] = Y1_a.e[1] = Y1_b.e[0] = Y1_b.e[1] = Y2_a.e[0] = Y2_a.e[1] = Y2_b.e[0] = Y2_b.e[1] = 0.0; }
   const int jm = (j == 0) ? ny - 1 : j - 1, jq = (j + 2 == ny) ? 0 : j + 2;
-  const size_t ra = base + (size_t)i * ny, rbo = ra + ny;
   double rl_a = 0.0, rl_b = 0.0, rr_a = 0.0, rr_b = 0.0, y1l_a = 0.0, y1l_b = 0.0, y2r_a = 0.0, y2r_b = 0.0;
   if (lane == 0) {
-    rl_a = ldg1(rho + ra + jm); rl_b = ldg1(rho + rbo + jm);
-    if (egno != 3) { y1l_a = ldg1(a1y + ra + jm); y1l_b = ldg1(a1y + rbo + jm); }
+    rl_a = ldg1(rho + (q.o_a + jm)); rl_b = ldg1(rho + (q.o_a + ny + jm));
+    if (egno != 3) { y1l_a = ldg1(a1y + (q.o_a + jm)); y1l_b = ldg1(a1y + (q.o_a + ny + jm)); }
   }
   if (lane == 31) {
-    rr_a = ldg1(rho + ra + jq); rr_b = ldg1(rho + rbo + jq);
-    if (egno != 3) { y2r_a = ldg1(a2y + ra + jq); y2r_b = ldg1(a2y + rbo + jq); }
+    rr_a = ldg1(rho + (q.o_a + jq)); rr_b = ldg1(rho + (q.o_a + ny + jq));
+    if (egno != 3) { y2r_a = ldg1(a2y + (q.o_a + jq)); y2r_b = ldg1(a2y + (q.o_a + ny + jq)); }
   }
   {
     double t;
@@ -358,15 +376,23 @@ __device__ __forceinline__ void cont_pair2d(const Ctx& c, const double* rho, con
       t = __shfl_down_sync(0xffffffffu, Y2_b.e[0], 1); if (lane != 31) y2r_b = t;
     }
   }
-  const double cx_a = c.cx()[i], cx_b = c.cx()[i + 1], cx_am = c.cx()[ba.m], cx_bp = c.cx()[bb.p];
-  const bool last = (k == K - 1);
+  if (!MATH) {     // profiling aid: same loads and shuffles, trivial arithmetic
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      xa.e[e] = R_a.e[e] + Rn_a.e[e] + R_m.e[e] + X1_a.e[e] + X1_m.e[e] + X2_a.e[e] + Y1_a.e[e] + Y2_a.e[e] + rl_a + rr_a + y1l_a + y2r_a;
+      xb.e[e] = R_b.e[e] + Rn_b.e[e] + R_p.e[e] + X1_b.e[e] + X2_b.e[e] + X2_p.e[e] + Y1_b.e[e] + Y2_b.e[e] + rl_b + rr_b + y1l_b + y2r_b;
+    }
+    return;
+  }
+  const Nbr ba = nbr(q.i, nx, a.p.bc_x), bb = nbr(q.i + 1, nx, a.p.bc_x);
+  const double cx_a = c.cx()[q.i], cx_b = c.cx()[q.i + 1], cx_am = c.cx()[ba.m], cx_bp = c.cx()[bb.p];
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     const double cy0 = c.cy()[j + e], cym = c.cy()[(e == 0) ? jm : j], cyp = c.cy()[(e == 1) ? jq : j + 1];
-    xa.e[e] = cont_point<2>(egno, last, R_a.e[e], Rn_a.e[e], (e == 0) ? rl_a : R_a.e[0], (e == 1) ? rr_a : R_a.e[1], R_m.e[e], R_b.e[e],
+    xa.e[e] = cont_point<2>(egno, q.last, R_a.e[e], Rn_a.e[e], (e == 0) ? rl_a : R_a.e[0], (e == 1) ? rr_a : R_a.e[1], R_m.e[e], R_b.e[e],
                             Y1_a.e[e], (e == 0) ? y1l_a : Y1_a.e[0], Y2_a.e[e], (e == 1) ? y2r_a : Y2_a.e[1], X1_a.e[e], X1_m.e[e],
                             X2_a.e[e], X2_b.e[e], cy0, cym, cyp, cx_a, cx_am, cx_b, ba.wm, ba.wp, epsl, rc, c_dt);
-    xb.e[e] = cont_point<2>(egno, last, R_b.e[e], Rn_b.e[e], (e == 0) ? rl_b : R_b.e[0], (e == 1) ? rr_b : R_b.e[1], R_a.e[e], R_p.e[e],
+    xb.e[e] = cont_point<2>(egno, q.last, R_b.e[e], Rn_b.e[e], (e == 0) ? rl_b : R_b.e[0], (e == 1) ? rr_b : R_b.e[1], R_a.e[e], R_p.e[e],
                             Y1_b.e[e], (e == 0) ? y1l_b : Y1_b.e[0], Y2_b.e[e], (e == 1) ? y2r_b : Y2_b.e[1], X1_b.e[e], X1_a.e[e],
                             X2_b.e[e], X2_p.e[e], cy0, cym, cyp, cx_b, cx_a, cx_bp, bb.wm, bb.wp, epsl, rc, c_dt);
   }
@@ -506,22 +532,41 @@ __device__ __noinline__ void phase_A_w256(Ctx& c, int cd, double epsl) {
   const int src = (lane & 16) | ((16 - jj) & 15);
   const int nwt = gridDim.x * kWarps;
   const bool paired = (ND == 2) && ((nx & 1) == 0);     // rows 2p, 2p+1 of a unit are x-neighbours in the same time row
+  const bool pf = paired && ((nx & 3) == 0) && a.pf_l2;
+  // profiling aid (MODE_PHASE only): bit 0 residual rounds, bit 1 transform, bit 2 split + transposed store, bit 3 rotate chunk order
+  const int dm = (a.mode == MODE_PHASE) ? a.dbg_pass : 7;
   for (int u = warp * gridDim.x + blockIdx.x; u < nunits; u += nwt) {
     const int r0 = 4 * u;
+    if (pf) {
+      // the unit's input rows (4 rows of 5 arrays, the next time row of rho, 4 halo rows) are requested from L2 up front:
+      // only the first of the 8 load rounds below then waits for DRAM
+      const int k0 = fast_div_exact(r0, nx, c.inv_nx), i0 = r0 - k0 * nx;
+      const size_t n_ = (size_t)nx * ny, o = (size_t)k0 * n_ + (size_t)i0 * ny;
+      const unsigned blk = 4u * ny * 8u, row = ny * 8u;
+      bulk_prefetch_l2(rho + o, blk); bulk_prefetch_l2(a1x + o, blk); bulk_prefetch_l2(a2x + o, blk);
+      if (EG != 3) { bulk_prefetch_l2(a1y + o, blk); bulk_prefetch_l2(a2y + o, blk); }
+      if (k0 + 1 < K) bulk_prefetch_l2(rho + o + n_, blk);
+      const int im = (i0 == 0) ? nx - 1 : i0 - 1, ip = (i0 + 4 == nx) ? 0 : i0 + 4;
+      const size_t om = (size_t)k0 * n_ + (size_t)im * ny, op = (size_t)k0 * n_ + (size_t)ip * ny;
+      bulk_prefetch_l2(rho + om, row); bulk_prefetch_l2(a1x + om, row); bulk_prefetch_l2(rho + op, row); bulk_prefetch_l2(a2x + op, row);
+    }
     __syncwarp();
 #pragma unroll 1
-    for (int pp = 0; pp < 2; ++pp) {
+    for (int pp = 0; pp < ((dm & 1) ? 2 : 0); ++pp) {
       const int ra = r0 + 2 * pp, rbw = ra + 1;
       const bool va = ra < rows, vb = rbw < rows;
       const int ka = fast_div_exact(va ? ra : 0, nx, c.inv_nx), ia = (va ? ra : 0) - ka * nx;
       const int kb = fast_div_exact(vb ? rbw : 0, nx, c.inv_nx), ib = (vb ? rbw : 0) - kb * nx;
+      PairRows prw;
+      if (ND == 2 && paired) prw = pair_rows(ka, ia);
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int c0 = 0; c0 < 4; ++c0) {
+        const int cc = (dm & 8) ? ((c0 + u) & 3) : c0;
         const int j = 2 * lane + 64 * cc;
         Vec<2> xa, xb;
         xa.e[0] = xa.e[1] = xb.e[0] = xb.e[1] = 0.0;
         if (ND == 2 && paired) {
-          if (va) cont_pair2d<EG>(c, rho, a1x, a2x, a1y, a2y, ka, ia, j, lane, epsl, rc, c_dt, xa, xb);     // (va == vb, warp-uniform)
+          if (va) cont_pair2d<EG>(c, rho, a1x, a2x, a1y, a2y, prw, j, lane, epsl, rc, c_dt, xa, xb);     // (va == vb, warp-uniform)
         } else {
           if (va) xa = cont_item<ND, 2, EG>(c, rho, a1x, a2x, a1y, a2y, ka, ia, j, epsl, rc, c_dt);
           if (vb) xb = cont_item<ND, 2, EG>(c, rho, a1x, a2x, a1y, a2y, kb, ib, j, epsl, rc, c_dt);
@@ -535,7 +580,8 @@ __device__ __noinline__ void phase_A_w256(Ctx& c, int cd, double epsl) {
     double2 v[16];
 #pragma unroll
     for (int t = 0; t < 16; ++t) v[t] = rb[jj + 17 * t];
-    wfft256<false>(v, rb, jj, c.twy());
+    if (dm & 2) wfft256<false>(v, rb, jj, c.twy());
+    if (!(dm & 4)) continue;
     // split: Z_a[m] = (X[m] + conj X[N-m]) / 2, Z_b[m] = (X[m] - conj X[N-m]) / (2i), m = jj + 16 q <= 128
     const int ra = r0 + 2 * pr, rbw = ra + 1;
     const bool va = ra < rows, vb = rbw < rows;
@@ -1596,7 +1642,7 @@ static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   if (g.d_pipe && smD > work) work = smD;
   // warp-private 256-point transforms: two padded rows per warp
   const size_t smW = (size_t)kWarps * 2 * kW256Ld * 16;
-  const bool w256 = getenv("PDHG_NO_W256") == nullptr && smW <= cap;
+  const bool w256 = getenv("PDHG_NO_W256") == nullptr && smW <= cap && (size_t)p.K * g.nxe * g.nye < ((size_t)1 << 31);
   // (a unit is one warp's work; below ~8 units per SM the tiled path, which spreads one tile over a whole CTA, is faster)
   const bool force = getenv("PDHG_FORCE_W256") != nullptr;
   const bool many_y = force || (rows + 3) / 4 >= 8 * sm_count, many_x = force || (p.K * g.nyh + 1) / 2 >= 8 * sm_count;
@@ -1666,7 +1712,7 @@ static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, 
   a.p = p;
   a.w = carve(p, ws);
   a.b = b; a.mode = mode; a.A = 2 * p.ndim;
-  a.nxe = g.nxe; a.nye = g.nye; a.nyh = g.nyh; a.TR = g.TR; a.TKY = g.TKY; a.d_pipe = g.d_pipe; a.fast_y = g.fast_y; a.fast_x = g.fast_x;
+  a.nxe = g.nxe; a.nye = g.nye; a.nyh = g.nyh; a.TR = g.TR; a.TKY = g.TKY; a.d_pipe = g.d_pipe; a.fast_y = g.fast_y; a.fast_x = g.fast_x; a.pf_l2 = getenv("PDHG_PF") != nullptr;
   a.has_x = (p.ndim == 2);
   if (p.ndim == 1) {
     a.dxe = 1.0; a.dye = p.dx; a.coef_xe = p.coef_x; a.coef_ye = p.coef_x; a.tw_xe = p.tw_x; a.tw_ye = p.tw_x;

@@ -21,8 +21,8 @@ def _single(rx, sf, nx, ny, epsl, T, stepsz, nmax):
   return fns, x_arr, res[0], info
 
 
-@pytest.mark.parametrize("P,nx,ny,epsl,nmax,stepsz", [(2, 32, 24, 0.0, 5000, 0.1), (4, 64, 32, 0.05, 300, 0.05), (3, 48, 16, 0.1, 60, 0.05),
-                                                        (1, 16, 16, 0.0, 40, 0.1), (2, 32, 24, 0.0, 400, 0.1), (2, 256, 256, 0.0, 12, 0.1), (4, 24, 256, 0.02, 12, 0.05)])
+@pytest.mark.parametrize("P,nx,ny,epsl,nmax,stepsz", [(2, 32, 24, 0.0, 5000, 0.1), (4, 64, 32, 0.05, 40, 0.05), (3, 48, 16, 0.1, 60, 0.05),
+                                                        (1, 16, 16, 0.0, 40, 0.1), (2, 32, 24, 0.0, 50, 0.1), (2, 256, 256, 0.0, 12, 0.1), (4, 24, 256, 0.02, 12, 0.05)])
 def test_slab_decomposition_equals_single_gpu_solve(built_lib, P, nx, ny, epsl, nmax, stepsz):
   from pdhg_b200 import run_example as rx, set_fns as sf, slab
   from pdhg_b200.set_fns import set_up_J
