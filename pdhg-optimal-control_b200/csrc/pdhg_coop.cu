@@ -23,7 +23,7 @@ namespace cg = cooperative_groups;
 
 namespace pdhg {
 
-constexpr int kNQ = 20;        // reduced quantities per epoch
+constexpr int kNQ = 36;        // reduced quantities per epoch: 0..15 dual sweep, 16..18 primal, 20..35 second sweep of a fused pair
 #ifndef PDHG_COOP_THREADS
 #define PDHG_COOP_THREADS 512
 #endif
@@ -37,8 +37,8 @@ constexpr int kWarps = kThreads / 32;
 struct CoopWs {
   double* phi[2];     // ping-pong phi [(K+1) n]
   double* phib;       // phi_bar [(K+1) n]
-  double* rho[2];     // ping-pong rho [K n]
-  double* alp[2];     // ping-pong alp [A][K n]
+  double* rho[3];     // rho [K n]: current outer iterate + two work buffers of the inner dual loop
+  double* alp[3];     // alp [A][K n], same roles
   double2* zt;        // [K][nyh][nx] half spectrum, transposed
   double* partials;   // [2][grid][kNQ]
   double* den;        // [K][nyh][nx]  reciprocal Thomas pivots (K > 1)
@@ -64,7 +64,7 @@ struct CoopArgs {
   int dbg_phase, dbg_pass;   // MODE_PHASE (profiling): phase id 0..3 = A,B,C,D and pass mask of phase B (bit 0,1,2)
   int d_pipe;         // 1: cp.async-pipelined dual sweep (ny even and the staging buffers fit shared memory)
   int fast_y, fast_x; // warp-private 256-point transforms along y (phases A, C) / along x (phase B)
-  int pf_l2;          // bulk L2 prefetch of a unit's input rows (opt-in PDHG_PF=1: measured slower)
+  int d_fuse;         // fuse two inner dual sweeps per pass while the inner loop is long (PDHG_NO_DFUSE disables)
   double dxe, dye;
   const double* coef_xe;
   const double* coef_ye;
@@ -163,10 +163,6 @@ __device__ __forceinline__ void stg1(double* p, double v) {
 }
 __device__ __forceinline__ void stg2(void* p, double2 v) {
   asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(p)), "d"(v.x), "d"(v.y) : "memory");
-}
-// one instruction (warp-uniform operands) asks L2 to fetch `bytes` (multiple of 16) starting at the 16-byte aligned p
-__device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(bytes) : "memory");
 }
 template <int VW> __device__ __forceinline__ Vec<VW> ldv(const double* p) {
   Vec<VW> r;
@@ -319,49 +315,36 @@ __device__ __forceinline__ Vec<VW> cont_item(const Ctx& c, const double* rho, co
 // lanes cover 64 consecutive columns (j = j0 + 2 lane): the x-neighbour rows are shared between the two items (16 vector loads
 // instead of 20, all issued before the arithmetic) and the y-neighbours come from the adjacent lanes by shuffle (only the two
 // edge lanes load a halo word).  Same operands as two cont_item calls => bitwise the same results.  All 32 lanes must call.
-struct PairRows {             // per row pair (k, i), (k, i+1): what does not depend on the column (32-bit element offsets: K n < 2^31)
-  unsigned o_m, o_a, o_p;     // rows i-1, i, i+2 of time row k   (row i+1 = o_a + ny; next time row = + n)
-  int i;
-  bool last;
-};
-__device__ __forceinline__ PairRows pair_rows(int k, int i) {
-  const CoopArgs& a = cargs();
-  const int nx = a.nxe, ny = a.nye;
-  const unsigned base = (unsigned)k * (unsigned)(nx * ny);
-  const Nbr ba = nbr(i, nx, a.p.bc_x), bb = nbr(i + 1, nx, a.p.bc_x);
-  PairRows r;
-  r.o_m = base + (unsigned)(ba.m * ny); r.o_a = base + (unsigned)(i * ny); r.o_p = base + (unsigned)(bb.p * ny);
-  r.i = i;
-  r.last = (k == a.p.K - 1);
-  return r;
-}
-template <int EG, bool MATH = true>
+template <int EG>
 __device__ __forceinline__ void cont_pair2d(const Ctx& c, const double* rho, const double* a1x, const double* a2x, const double* a1y,
-                                            const double* a2y, const PairRows& q, int j, int lane, double epsl, const Recip& rc, double c_dt,
+                                            const double* a2y, int k, int i, int j, int lane, double epsl, const Recip& rc, double c_dt,
                                             Vec<2>& xa, Vec<2>& xb) {
   const CoopArgs& a = cargs();
-  const int nx = a.nxe, ny = a.nye;
-  const unsigned n = (unsigned)(nx * ny);
+  const MarchParams& p = a.p;
+  const int K = p.K, nx = a.nxe, ny = a.nye;
+  const size_t n = (size_t)nx * ny, base = (size_t)k * n;
   constexpr int egno = EG;
-  const unsigned jm_ = q.o_m + j, ja_ = q.o_a + j, jb_ = ja_ + ny, jp_ = q.o_p + j;
-  const Vec<2> R_m = ldv<2>(rho + jm_), R_a = ldv<2>(rho + ja_), R_b = ldv<2>(rho + jb_), R_p = ldv<2>(rho + jp_);
+  const Nbr ba = nbr(i, nx, p.bc_x), bb = nbr(i + 1, nx, p.bc_x);
+  const size_t o_m = base + (size_t)ba.m * ny + j, o_a = base + (size_t)i * ny + j, o_b = o_a + ny, o_p = base + (size_t)bb.p * ny + j;
+  const Vec<2> R_m = ldv<2>(rho + o_m), R_a = ldv<2>(rho + o_a), R_b = ldv<2>(rho + o_b), R_p = ldv<2>(rho + o_p);
   Vec<2> Rn_a, Rn_b;
-  if (!q.last) { Rn_a = ldv<2>(rho + (ja_ + n)); Rn_b = ldv<2>(rho + (jb_ + n)); }
+  if (k + 1 < K) { Rn_a = ldv<2>(rho + o_a + n); Rn_b = ldv<2>(rho + o_b + n); }
   else { Rn_a.e[0] = Rn_a.e[1] = Rn_b.e[0] = Rn_b.e[1] = 0.0; }
-  const Vec<2> X1_m = ldv<2>(a1x + jm_), X1_a = ldv<2>(a1x + ja_), X1_b = ldv<2>(a1x + jb_);
-  const Vec<2> X2_a = ldv<2>(a2x + ja_), X2_b = ldv<2>(a2x + jb_), X2_p = ldv<2>(a2x + jp_);
+  const Vec<2> X1_m = ldv<2>(a1x + o_m), X1_a = ldv<2>(a1x + o_a), X1_b = ldv<2>(a1x + o_b);
+  const Vec<2> X2_a = ldv<2>(a2x + o_a), X2_b = ldv<2>(a2x + o_b), X2_p = ldv<2>(a2x + o_p);
   Vec<2> Y1_a, Y1_b, Y2_a, Y2_b;
-  if (egno != 3) { Y1_a = ldv<2>(a1y + ja_); Y1_b = ldv<2>(a1y + jb_); Y2_a = ldv<2>(a2y + ja_); Y2_b = ldv<2>(a2y + jb_); }
+  if (egno != 3) { Y1_a = ldv<2>(a1y + o_a); Y1_b = ldv<2>(a1y + o_b); Y2_a = ldv<2>(a2y + o_a); Y2_b = ldv<2>(a2y + o_b); }
   else { Y1_a.e[0] = Y1_a.e[1] = Y1_b.e[0] = Y1_b.e[1] = Y2_a.e[0] = Y2_a.e[1] = Y2_b.e[0] = Y2_b.e[1] = 0.0; }
   const int jm = (j == 0) ? ny - 1 : j - 1, jq = (j + 2 == ny) ? 0 : j + 2;
+  const size_t ra = base + (size_t)i * ny, rbo = ra + ny;
   double rl_a = 0.0, rl_b = 0.0, rr_a = 0.0, rr_b = 0.0, y1l_a = 0.0, y1l_b = 0.0, y2r_a = 0.0, y2r_b = 0.0;
   if (lane == 0) {
-    rl_a = ldg1(rho + (q.o_a + jm)); rl_b = ldg1(rho + (q.o_a + ny + jm));
-    if (egno != 3) { y1l_a = ldg1(a1y + (q.o_a + jm)); y1l_b = ldg1(a1y + (q.o_a + ny + jm)); }
+    rl_a = ldg1(rho + ra + jm); rl_b = ldg1(rho + rbo + jm);
+    if (egno != 3) { y1l_a = ldg1(a1y + ra + jm); y1l_b = ldg1(a1y + rbo + jm); }
   }
   if (lane == 31) {
-    rr_a = ldg1(rho + (q.o_a + jq)); rr_b = ldg1(rho + (q.o_a + ny + jq));
-    if (egno != 3) { y2r_a = ldg1(a2y + (q.o_a + jq)); y2r_b = ldg1(a2y + (q.o_a + ny + jq)); }
+    rr_a = ldg1(rho + ra + jq); rr_b = ldg1(rho + rbo + jq);
+    if (egno != 3) { y2r_a = ldg1(a2y + ra + jq); y2r_b = ldg1(a2y + rbo + jq); }
   }
   {
     double t;
@@ -376,23 +359,15 @@ __device__ __forceinline__ void cont_pair2d(const Ctx& c, const double* rho, con
       t = __shfl_down_sync(0xffffffffu, Y2_b.e[0], 1); if (lane != 31) y2r_b = t;
     }
   }
-  if (!MATH) {     // profiling aid: same loads and shuffles, trivial arithmetic
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      xa.e[e] = R_a.e[e] + Rn_a.e[e] + R_m.e[e] + X1_a.e[e] + X1_m.e[e] + X2_a.e[e] + Y1_a.e[e] + Y2_a.e[e] + rl_a + rr_a + y1l_a + y2r_a;
-      xb.e[e] = R_b.e[e] + Rn_b.e[e] + R_p.e[e] + X1_b.e[e] + X2_b.e[e] + X2_p.e[e] + Y1_b.e[e] + Y2_b.e[e] + rl_b + rr_b + y1l_b + y2r_b;
-    }
-    return;
-  }
-  const Nbr ba = nbr(q.i, nx, a.p.bc_x), bb = nbr(q.i + 1, nx, a.p.bc_x);
-  const double cx_a = c.cx()[q.i], cx_b = c.cx()[q.i + 1], cx_am = c.cx()[ba.m], cx_bp = c.cx()[bb.p];
+  const double cx_a = c.cx()[i], cx_b = c.cx()[i + 1], cx_am = c.cx()[ba.m], cx_bp = c.cx()[bb.p];
+  const bool last = (k == K - 1);
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     const double cy0 = c.cy()[j + e], cym = c.cy()[(e == 0) ? jm : j], cyp = c.cy()[(e == 1) ? jq : j + 1];
-    xa.e[e] = cont_point<2>(egno, q.last, R_a.e[e], Rn_a.e[e], (e == 0) ? rl_a : R_a.e[0], (e == 1) ? rr_a : R_a.e[1], R_m.e[e], R_b.e[e],
+    xa.e[e] = cont_point<2>(egno, last, R_a.e[e], Rn_a.e[e], (e == 0) ? rl_a : R_a.e[0], (e == 1) ? rr_a : R_a.e[1], R_m.e[e], R_b.e[e],
                             Y1_a.e[e], (e == 0) ? y1l_a : Y1_a.e[0], Y2_a.e[e], (e == 1) ? y2r_a : Y2_a.e[1], X1_a.e[e], X1_m.e[e],
                             X2_a.e[e], X2_b.e[e], cy0, cym, cyp, cx_a, cx_am, cx_b, ba.wm, ba.wp, epsl, rc, c_dt);
-    xb.e[e] = cont_point<2>(egno, q.last, R_b.e[e], Rn_b.e[e], (e == 0) ? rl_b : R_b.e[0], (e == 1) ? rr_b : R_b.e[1], R_a.e[e], R_p.e[e],
+    xb.e[e] = cont_point<2>(egno, last, R_b.e[e], Rn_b.e[e], (e == 0) ? rl_b : R_b.e[0], (e == 1) ? rr_b : R_b.e[1], R_a.e[e], R_p.e[e],
                             Y1_b.e[e], (e == 0) ? y1l_b : Y1_b.e[0], Y2_b.e[e], (e == 1) ? y2r_b : Y2_b.e[1], X1_b.e[e], X1_a.e[e],
                             X2_b.e[e], X2_p.e[e], cy0, cym, cyp, cx_b, cx_a, cx_bp, bb.wm, bb.wp, epsl, rc, c_dt);
   }
@@ -532,41 +507,22 @@ __device__ __noinline__ void phase_A_w256(Ctx& c, int cd, double epsl) {
   const int src = (lane & 16) | ((16 - jj) & 15);
   const int nwt = gridDim.x * kWarps;
   const bool paired = (ND == 2) && ((nx & 1) == 0);     // rows 2p, 2p+1 of a unit are x-neighbours in the same time row
-  const bool pf = paired && ((nx & 3) == 0) && a.pf_l2;
-  // profiling aid (MODE_PHASE only): bit 0 residual rounds, bit 1 transform, bit 2 split + transposed store, bit 3 rotate chunk order
-  const int dm = (a.mode == MODE_PHASE) ? a.dbg_pass : 7;
   for (int u = warp * gridDim.x + blockIdx.x; u < nunits; u += nwt) {
     const int r0 = 4 * u;
-    if (pf) {
-      // the unit's input rows (4 rows of 5 arrays, the next time row of rho, 4 halo rows) are requested from L2 up front:
-      // only the first of the 8 load rounds below then waits for DRAM
-      const int k0 = fast_div_exact(r0, nx, c.inv_nx), i0 = r0 - k0 * nx;
-      const size_t n_ = (size_t)nx * ny, o = (size_t)k0 * n_ + (size_t)i0 * ny;
-      const unsigned blk = 4u * ny * 8u, row = ny * 8u;
-      bulk_prefetch_l2(rho + o, blk); bulk_prefetch_l2(a1x + o, blk); bulk_prefetch_l2(a2x + o, blk);
-      if (EG != 3) { bulk_prefetch_l2(a1y + o, blk); bulk_prefetch_l2(a2y + o, blk); }
-      if (k0 + 1 < K) bulk_prefetch_l2(rho + o + n_, blk);
-      const int im = (i0 == 0) ? nx - 1 : i0 - 1, ip = (i0 + 4 == nx) ? 0 : i0 + 4;
-      const size_t om = (size_t)k0 * n_ + (size_t)im * ny, op = (size_t)k0 * n_ + (size_t)ip * ny;
-      bulk_prefetch_l2(rho + om, row); bulk_prefetch_l2(a1x + om, row); bulk_prefetch_l2(rho + op, row); bulk_prefetch_l2(a2x + op, row);
-    }
     __syncwarp();
 #pragma unroll 1
-    for (int pp = 0; pp < ((dm & 1) ? 2 : 0); ++pp) {
+    for (int pp = 0; pp < 2; ++pp) {
       const int ra = r0 + 2 * pp, rbw = ra + 1;
       const bool va = ra < rows, vb = rbw < rows;
       const int ka = fast_div_exact(va ? ra : 0, nx, c.inv_nx), ia = (va ? ra : 0) - ka * nx;
       const int kb = fast_div_exact(vb ? rbw : 0, nx, c.inv_nx), ib = (vb ? rbw : 0) - kb * nx;
-      PairRows prw;
-      if (ND == 2 && paired) prw = pair_rows(ka, ia);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 4; ++c0) {
-        const int cc = (dm & 8) ? ((c0 + u) & 3) : c0;
+      for (int cc = 0; cc < 4; ++cc) {
         const int j = 2 * lane + 64 * cc;
         Vec<2> xa, xb;
         xa.e[0] = xa.e[1] = xb.e[0] = xb.e[1] = 0.0;
         if (ND == 2 && paired) {
-          if (va) cont_pair2d<EG>(c, rho, a1x, a2x, a1y, a2y, prw, j, lane, epsl, rc, c_dt, xa, xb);     // (va == vb, warp-uniform)
+          if (va) cont_pair2d<EG>(c, rho, a1x, a2x, a1y, a2y, ka, ia, j, lane, epsl, rc, c_dt, xa, xb);     // (va == vb, warp-uniform)
         } else {
           if (va) xa = cont_item<ND, 2, EG>(c, rho, a1x, a2x, a1y, a2y, ka, ia, j, epsl, rc, c_dt);
           if (vb) xb = cont_item<ND, 2, EG>(c, rho, a1x, a2x, a1y, a2y, kb, ib, j, epsl, rc, c_dt);
@@ -580,8 +536,7 @@ __device__ __noinline__ void phase_A_w256(Ctx& c, int cd, double epsl) {
     double2 v[16];
 #pragma unroll
     for (int t = 0; t < 16; ++t) v[t] = rb[jj + 17 * t];
-    if (dm & 2) wfft256<false>(v, rb, jj, c.twy());
-    if (!(dm & 4)) continue;
+    wfft256<false>(v, rb, jj, c.twy());
     // split: Z_a[m] = (X[m] + conj X[N-m]) / 2, Z_b[m] = (X[m] - conj X[N-m]) / (2i), m = jj + 16 q <= 128
     const int ra = r0 + 2 * pr, rbw = ra + 1;
     const bool va = ra < rows, vb = rbw < rows;
@@ -1004,7 +959,10 @@ __device__ __forceinline__ void dual_point(int egno, double c0, double cxm, doub
 
 // ---- phase D: one dual sweep.  src -> dst (may alias); outer differences against `ref` when HASREF.
 // CTA partials: slots 0..1 rho (diff^2, next^2), 2+2q..3+2q alp q; 10 outer rho diff^2, 11+q outer alp diff^2; 15 NaN count of rho_next
-template <int ND, int VW, bool HASREF, int EG>
+// NS = 2 fuses two consecutive sweeps into one pass over memory: the dual update at a point needs phi_bar's stencil but only the
+// point's own rho / alp, so the second sweep runs on the first one's results while they are still in registers (same arithmetic
+// per point, same per-thread summation order => bit-identical iterates and error sums; its sums go to slots 20..35).
+template <int ND, int VW, bool HASREF, int EG, int NS = 1>
 __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d, double* alp_d,
                         const double* rho_ref, const double* alp_ref, double sigma, double epsl) {
   phib = as_global(phib); rho_s = as_global(rho_s); alp_s = as_global(alp_s); rho_d = as_global(rho_d); alp_d = as_global(alp_d);
@@ -1019,8 +977,9 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
   const int ny2 = ny / VW;
   double s_dr = 0.0, s_rr = 0.0, s_or = 0.0, s_nan = 0.0;
   double s_da[NA], s_aa[NA], s_oa[NA];
+  double t_dr = 0.0, t_rr = 0.0, t_nan = 0.0, t_da[NA], t_aa[NA];      // second sweep of a fused pair (NS == 2)
 #pragma unroll
-  for (int q = 0; q < NA; ++q) { s_da[q] = 0.0; s_aa[q] = 0.0; s_oa[q] = 0.0; }
+  for (int q = 0; q < NA; ++q) { s_da[q] = 0.0; s_aa[q] = 0.0; s_oa[q] = 0.0; t_da[q] = 0.0; t_aa[q] = 0.0; }
   // thread-linear grid-stride over VW-wide items: consecutive threads of a CTA take consecutive items of a row
   const float inv_ny2 = 1.0f / (float)ny2;
   const long long items = (long long)K * nx * ny2, istride = (long long)gridDim.x * blockDim.x;
@@ -1058,9 +1017,6 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
       for (int q = 0; q < NA; ++q) aoe[q] = ao[q].e[e];
       dual_point<ND>(egno, cc.e[e], (ND == 2) ? cxm.e[e] : 0.0, (ND == 2) ? cxp.e[e] : 0.0, cym, cyp, pk.e[e], ro.e[e], aoe, cx,
                      c.cy()[j + e], bx.wm, bx.wp, sigma, epsl, rc, rne, ane);
-      rn.e[e] = rne;
-#pragma unroll
-      for (int q = 0; q < NA; ++q) an[q].e[e] = ane[q];
       if (acc_on) {
         double d = rne - ro.e[e];
         s_dr += d * d; s_rr += rne * rne; s_nan += is_nan(rne) ? 1.0 : 0.0;
@@ -1072,6 +1028,23 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
           if (HASREF) { d = ane[q] - aref[q].e[e]; s_oa[q] += d * d; }
         }
       }
+      if (NS == 2) {
+        double an2[NA], rn2;
+        dual_point<ND>(egno, cc.e[e], (ND == 2) ? cxm.e[e] : 0.0, (ND == 2) ? cxp.e[e] : 0.0, cym, cyp, pk.e[e], rne, ane, cx,
+                       c.cy()[j + e], bx.wm, bx.wp, sigma, epsl, rc, rn2, an2);
+        if (acc_on) {
+          double d = rn2 - rne;
+          t_dr += d * d; t_rr += rn2 * rn2; t_nan += is_nan(rn2) ? 1.0 : 0.0;
+#pragma unroll
+          for (int q = 0; q < NA; ++q) { d = an2[q] - ane[q]; t_da[q] += d * d; t_aa[q] += an2[q] * an2[q]; }
+        }
+        rne = rn2;
+#pragma unroll
+        for (int q = 0; q < NA; ++q) ane[q] = an2[q];
+      }
+      rn.e[e] = rne;
+#pragma unroll
+      for (int q = 0; q < NA; ++q) an[q].e[e] = ane[q];
     }
     stv<VW>(rho_d + g, rn);
 #pragma unroll
@@ -1085,6 +1058,14 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
 #pragma unroll
   for (int q = 0; q < NA; ++q) { sums[2 + 2 * q] = s_da[q]; sums[3 + 2 * q] = s_aa[q]; sums[11 + q] = s_oa[q]; }
   cta_partials<16>(c, sums, 0);
+  if (NS == 2) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) sums[q] = 0.0;
+    sums[0] = t_dr; sums[1] = t_rr; sums[15] = t_nan;
+#pragma unroll
+    for (int q = 0; q < NA; ++q) { sums[2 + 2 * q] = t_da[q]; sums[3 + 2 * q] = t_aa[q]; }
+    cta_partials<16>(c, sums, 20);
+  }
 }
 
 // ---- phase D, software-pipelined: every warp stages the inputs of its NEXT (row, 64-point chunk) unit in shared memory
@@ -1286,8 +1267,15 @@ __device__ __forceinline__ void run_C(Ctx& c, const double* pp, double* pn, doub
 }
 template <int EG>
 __device__ __forceinline__ void run_D_eg(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d, double* alp_d,
-                                         const double* rho_ref, const double* alp_ref, double sigma, double epsl) {
+                                         const double* rho_ref, const double* alp_ref, double sigma, double epsl, int ns) {
   const bool v2 = (cargs().nye & 1) == 0;
+  if (ns == 2) {        // fused pair of sweeps (callers only ask for it without reference arrays)
+    if (cargs().has_x) { if (v2) phase_D<2, 2, false, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
+                         else phase_D<2, 1, false, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
+    else { if (v2) phase_D<1, 2, false, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
+           else phase_D<1, 1, false, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
+    return;
+  }
   if (rho_ref) {
     if (cargs().has_x) { if (v2) phase_D<2, 2, true, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
                          else phase_D<2, 1, true, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl); }
@@ -1301,8 +1289,8 @@ __device__ __forceinline__ void run_D_eg(Ctx& c, const double* phib, const doubl
   }
 }
 __device__ __forceinline__ void run_D(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d, double* alp_d,
-                                      const double* rho_ref, const double* alp_ref, double sigma, double epsl) {
-  if (cargs().d_pipe) {
+                                      const double* rho_ref, const double* alp_ref, double sigma, double epsl, int ns = 1) {
+  if (cargs().d_pipe && ns == 1) {
     if (rho_ref) { if (cargs().has_x) phase_D_pipe<2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
                    else phase_D_pipe<1, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl); }
     else { if (cargs().has_x) phase_D_pipe<2, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
@@ -1310,9 +1298,9 @@ __device__ __forceinline__ void run_D(Ctx& c, const double* phib, const double* 
     return;
   }
   const int eg = cargs().p.egno;
-  if (eg == 1) run_D_eg<1>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
-  else if (eg == 2) run_D_eg<2>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
-  else run_D_eg<3>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
+  if (eg == 1) run_D_eg<1>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl, ns);
+  else if (eg == 2) run_D_eg<2>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl, ns);
+  else run_D_eg<3>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl, ns);
 }
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -1471,7 +1459,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
         for (int q = 0; q < 4; ++q) S_alp[q] = v[2 + q];
       }
       long long it = p.iter_begin;
-      int reason = END_MAXITER, nrec = 0;
+      int reason = END_MAXITER, nrec = 0, prev_j = p.rho_alp_iters;
       bool lognan = false, logfull = false;
       double err1 = 0.0, err2 = 0.0, rmin = 0.0, rmax = 0.0;
 
@@ -1488,21 +1476,47 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
         run_C(c, w.phi[cp], w.phi[cp ^ 1], w.phib, tau);
         c.grid.sync();
         TICK(2);
-        // dual sweeps: the first goes cd -> cd^1, the rest in place on cd^1 with outer differences against cd
-        const int nd = cd ^ 1;
+        // dual sweeps (update_dual_alternative, update_fns_in_pdhg.py:167-180): buffer cd holds the outer iterate and stays intact
+        // (phase E needs it), the sweeps ping-pong between the two other buffers.  While the previous outer iteration needed
+        // several sweeps, two sweeps are fused per pass (phase_D<NS = 2>); when the exit test already holds after the first
+        // sweep of a pair, that single sweep is redone from the pair's (still intact) input, so iterates, sweep counts and
+        // error sums are exactly those of the sweep-by-sweep loop.
+        const int f1 = (cd + 1) % 3, f2 = (cd + 2) % 3;
         double e1s0 = 0.0, e1s1 = 0.0, e1nan = 0.0;
-        int j = 0;
-        for (; j < p.rho_alp_iters; ++j) {
-          if (j == 0) run_D(c, w.phib, w.rho[cd], w.alp[cd], w.rho[nd], w.alp[nd], nullptr, nullptr, sigma, epsl);
-          else run_D(c, w.phib, w.rho[nd], w.alp[nd], w.rho[nd], w.alp[nd], nullptr, nullptr, sigma, epsl);   // in place
+        int j = 0, last = cd;
+        while (j < p.rho_alp_iters) {
+          const int src = last, dst = (last == f1) ? f2 : f1;
+          const bool pair = a.d_fuse && (prev_j - j >= 2) && (j + 2 <= p.rho_alp_iters);
+          run_D(c, w.phib, w.rho[src], w.alp[src], w.rho[dst], w.alp[dst], nullptr, nullptr, sigma, epsl, pair ? 2 : 1);
           grid_gather(c, v);
           c.tick(9);
           if (j == 0) { e1s0 = v[16]; e1s1 = v[17]; e1nan = v[18]; }
           double err = v[0] / v[1];
 #pragma unroll
           for (int q = 0; q < 4; ++q) if (q < A) err += v[2 + 2 * q] / v[3 + 2 * q];
-          if (err < p.eps) { ++j; break; }
+          if (!pair) {
+            last = dst; ++j;
+            if (err < p.eps) break;
+            continue;
+          }
+          if (err < p.eps) {
+            // exit after the first sweep of the pair: redo exactly that sweep (same input, same arithmetic, same sums)
+            run_D(c, w.phib, w.rho[src], w.alp[src], w.rho[dst], w.alp[dst], nullptr, nullptr, sigma, epsl, 1);
+            grid_gather(c, v);
+            last = dst; ++j;
+            break;
+          }
+          // second sweep of the pair: its sums sit in slots 20..35; from here on v[0..15] describe the last sweep done
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = v[20 + q];
+          last = dst; j += 2;
+          err = v[0] / v[1];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (q < A) err += v[2 + 2 * q] / v[3 + 2 * q];
+          if (err < p.eps) break;
         }
+        prev_j = j;
+        const int nd = last;
         inner_total += j;
         const bool multi = (j > 1);
         double vo[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -1642,7 +1656,7 @@ static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   if (g.d_pipe && smD > work) work = smD;
   // warp-private 256-point transforms: two padded rows per warp
   const size_t smW = (size_t)kWarps * 2 * kW256Ld * 16;
-  const bool w256 = getenv("PDHG_NO_W256") == nullptr && smW <= cap && (size_t)p.K * g.nxe * g.nye < ((size_t)1 << 31);
+  const bool w256 = getenv("PDHG_NO_W256") == nullptr && smW <= cap;
   // (a unit is one warp's work; below ~8 units per SM the tiled path, which spreads one tile over a whole CTA, is faster)
   const bool force = getenv("PDHG_FORCE_W256") != nullptr;
   const bool many_y = force || (rows + 3) / 4 >= 8 * sm_count, many_x = force || (p.K * g.nyh + 1) / 2 >= 8 * sm_count;
@@ -1660,8 +1674,8 @@ size_t pdhg_coop_workspace_bytes(const MarchParams& p, int B) {
   const size_t n = (size_t)nxe * nye, KN = (size_t)p.K * n, NP = (size_t)(p.K + 1) * n, modes = (size_t)nyh * nxe;
   size_t bytes = 0;
   bytes += align_up(3 * NP * 8, 256);
-  bytes += align_up(2 * KN * 8, 256);
-  bytes += align_up(2 * A * KN * 8, 256);
+  bytes += align_up(3 * KN * 8, 256);
+  bytes += align_up(3 * A * KN * 8, 256);
   bytes += align_up((size_t)p.K * modes * 16, 256);
   bytes += align_up((size_t)2 * 1024 * kNQ * 8, 256);
   bytes += align_up(2 * (size_t)p.K * modes * 8, 256);
@@ -1674,8 +1688,8 @@ static CoopWs carve(const MarchParams& p, void* ws) {
   char* q = static_cast<char*>(ws);
   CoopWs w;
   w.phi[0] = (double*)q; w.phi[1] = w.phi[0] + NP; w.phib = w.phi[1] + NP; q += align_up(3 * NP * 8, 256);
-  w.rho[0] = (double*)q; w.rho[1] = w.rho[0] + KN; q += align_up(2 * KN * 8, 256);
-  w.alp[0] = (double*)q; w.alp[1] = w.alp[0] + (size_t)A * KN; q += align_up(2 * A * KN * 8, 256);
+  w.rho[0] = (double*)q; w.rho[1] = w.rho[0] + KN; w.rho[2] = w.rho[1] + KN; q += align_up(3 * KN * 8, 256);
+  w.alp[0] = (double*)q; w.alp[1] = w.alp[0] + (size_t)A * KN; w.alp[2] = w.alp[1] + (size_t)A * KN; q += align_up(3 * A * KN * 8, 256);
   w.zt = (double2*)q; q += align_up((size_t)p.K * modes * 16, 256);
   w.partials = (double*)q; q += align_up((size_t)2 * 1024 * kNQ * 8, 256);
   w.den = (double*)q; w.tu = w.den + (size_t)p.K * modes; q += align_up(2 * (size_t)p.K * modes * 8, 256);
@@ -1712,7 +1726,7 @@ static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, 
   a.p = p;
   a.w = carve(p, ws);
   a.b = b; a.mode = mode; a.A = 2 * p.ndim;
-  a.nxe = g.nxe; a.nye = g.nye; a.nyh = g.nyh; a.TR = g.TR; a.TKY = g.TKY; a.d_pipe = g.d_pipe; a.fast_y = g.fast_y; a.fast_x = g.fast_x; a.pf_l2 = getenv("PDHG_PF") != nullptr;
+  a.nxe = g.nxe; a.nye = g.nye; a.nyh = g.nyh; a.TR = g.TR; a.TKY = g.TKY; a.d_pipe = g.d_pipe; a.fast_y = g.fast_y; a.fast_x = g.fast_x; a.d_fuse = (getenv("PDHG_NO_DFUSE") == nullptr && !g.d_pipe) ? 1 : 0;
   a.has_x = (p.ndim == 2);
   if (p.ndim == 1) {
     a.dxe = 1.0; a.dye = p.dx; a.coef_xe = p.coef_x; a.coef_ye = p.coef_x; a.tw_xe = p.tw_x; a.tw_ye = p.tw_x;

@@ -16,7 +16,7 @@ import numpy as np
 from . import _dev, _lib
 from .set_fns import coef_tables
 
-NQ = 20
+NQ = 36      # kNQ of csrc/pdhg_coop.cu
 
 
 class SlabRank:
@@ -214,7 +214,8 @@ def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_ite
         R.ext(R.hB, 1, 0.0, epsl, zt=R.ztB, nyh_override=R.kyn, ky_off=R.ky0, nyh_tab=R.nyh)
     group.transpose_bwd()
     for R in ranks:
-      R.ext(R.hL, 2, tau, epsl, zt=R.zt, phi_in=R.phi[R.cp], phi_out=R.phi[R.cp ^ 1], phib=R.phib)
+      # phase C of the local handle normalises the inverse transforms by 1 / (nxp ny); the x-transform ran over the global nx
+      R.ext(R.hL, 2, tau * R.nxp / R.nx, epsl, zt=R.zt, phi_in=R.phi[R.cp], phi_out=R.phi[R.cp ^ 1], phib=R.phib)
     group.halo(lambda R: [R.phib])
     j = 0
     while j < rho_alp_iters:

@@ -35,6 +35,27 @@ __global__ void __launch_bounds__(TPB, CPS) rd(const double2* base, size_t n2, d
   if (acc == 1.2345) out[0] = acc;
 }
 
+
+// L2 re-read test: every thread loads its element and the same element of the rows above / below (row = 128 double2 = 2 KB):
+// DRAM traffic 1x, L2 -> L1 traffic NB x (the neighbour rows are fetched by other CTAs at about the same time => L2 hits)
+template <int NA, int NB, int OFF>
+__global__ void __launch_bounds__(512, 1) rd_nbr(const double2* base, size_t n2, double* out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x + (size_t)OFF * NB; g + (size_t)OFF * NB < n2; g += stride) {
+    double2 v[NA][NB];
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) v[a][b] = ldg2(base + (size_t)a * n2 + g + (size_t)(b - NB / 2) * OFF);
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) acc += v[a][b].x * v[a][b].y;
+  }
+  if (acc == 1.2345) out[0] = acc;
+}
+
 // D-like: read NR arrays, write NW arrays, FL dependent DFMA per element pair in between
 template <int NR, int NW, int UN, int FL, int TPB, int CPS>
 __global__ void __launch_bounds__(TPB, CPS) rw(const double2* base, double2* obase, size_t n2) {
@@ -144,8 +165,20 @@ int main() {
   RD(6, 1, 512, 2) RD(6, 2, 512, 2) RD(6, 4, 512, 2)
   RD(6, 1, 1024, 2) RD(6, 2, 1024, 2)
   RD(1, 8, 512, 1) RD(1, 16, 512, 1) RD(1, 8, 1024, 2)
+#define RN(NA, NB, OFF) { float ms = time_it([&] { rd_nbr<NA, NB, OFF><<<sms, 512>>>(in, n2, o); }); \
+    printf("nbr   %2d arrays x %d copies, offset %6d: %7.1f us  unique %6.0f GB/s  loads %6.0f GB/s\n", NA, NB, OFF, ms * 1e3, NA * n * 8 / ms / 1e6, NA * NB * n * 8 / ms / 1e6); }
+  RN(6, 1, 128) RN(6, 3, 128) RN(6, 2, 18944) RN(6, 3, 18944) RN(4, 3, 18944) RN(2, 5, 18944) RN(2, 3, 18944) RN(6, 3, 3200) RN(2, 5, 3200)
 #define RW(NR, NW, UN, FL, TPB, CPS) { float ms = time_it([&] { rw<NR, NW, UN, FL, TPB, CPS><<<sms * CPS, TPB>>>(in, outb, n2); }); \
     printf("r/w   %2d in %d out, x%d, %3d dfma: %4d thr x %d CTA/SM: %7.1f us  %6.0f GB/s\n", NR, NW, UN, FL, TPB, CPS, ms * 1e3, (NR + NW) * n * 8 / ms / 1e6); }
+  { cudaFuncSetAttribute(rw<7, 5, 1, 100, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    float ms = time_it([&] { rw<7, 5, 1, 100, 512, 1><<<sms, 512, 160 * 1024>>>(in, outb, n2); });
+    printf("r/w 7 in 5 out x1 100 dfma with 160 KB dynamic smem (L1 = 92 KB): %7.1f us  %6.0f GB/s\n", ms * 1e3, 12 * n * 8 / ms / 1e6);
+    cudaFuncSetAttribute(rd<6, 2, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    ms = time_it([&] { rd<6, 2, 512, 1><<<sms, 512, 160 * 1024>>>(in, n2, o); });
+    printf("read 6 arrays x2 with 160 KB dynamic smem: %7.1f us  %6.0f GB/s\n", ms * 1e3, 6 * n * 8 / ms / 1e6);
+    cudaFuncSetAttribute(rd_nbr<6, 3, 18944>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    ms = time_it([&] { rd_nbr<6, 3, 18944><<<sms, 512, 160 * 1024>>>(in, n2, o); });
+    printf("nbr 6 x 3 with 160 KB dynamic smem: %7.1f us  %6.0f GB/s\n", ms * 1e3, 6 * n * 8 / ms / 1e6); }
   RW(7, 5, 1, 0, 512, 1) RW(7, 5, 2, 0, 512, 1) RW(7, 5, 1, 100, 512, 1) RW(7, 5, 2, 100, 512, 1) RW(7, 5, 1, 0, 512, 2) RW(7, 5, 2, 0, 512, 2)
   RW(7, 5, 1, 100, 512, 2) RW(7, 5, 1, 0, 1024, 2) RW(7, 5, 1, 100, 1024, 2) RW(2, 2, 4, 0, 512, 1) RW(2, 2, 8, 0, 512, 1)
 #define TR(ST, CH) { cudaFuncSetAttribute(tma_ring<ST, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + ST * CH); \

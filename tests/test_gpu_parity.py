@@ -189,7 +189,7 @@ def test_cfg3_grid_first_iterations_vs_oracle(pk):
   assert relmax(errs[0], errs_o[0]) < 1e-7 and info["block_iters"] == [25]
 
 
-@pytest.mark.parametrize("ndim,nx,ny,nt,epsl,nmax", [(2, 256, 256, 4, 0.002, 6), (2, 64, 256, 3, 0.0, 8), (2, 256, 48, 3, 0.005, 8), (1, 256, 1, 4, 0.003, 40),
+@pytest.mark.parametrize("ndim,nx,ny,nt,epsl,nmax", [(2, 256, 256, 4, 0.002, 6), (2, 64, 256, 3, 0.0, 8), (2, 256, 48, 3, 0.005, 8), (2, 32, 64, 5, 0.01, 12), (1, 256, 1, 4, 0.003, 40),
                                                        (1, 256, 1, 6, 0.0, 30)])
 def test_warp_private_256_point_transforms_vs_oracle(pk, ndim, nx, ny, nt, epsl, nmax):
   """The barrier-free 256-point fast path of the cooperative kernel (phases A/C when ny == 256, phase B when nx == 256; 1-D
@@ -204,10 +204,13 @@ def test_warp_private_256_point_transforms_vs_oracle(pk, ndim, nx, ny, nt, epsl,
   T = (nt - 1) / 64.0
   os.environ["PDHG_FORCE_PATH"] = "2"
   try:
-    for env in ("PDHG_FORCE_W256", "PDHG_NO_W256"):     # (by default the fast path is only taken when there are >= 8 units per SM)
-      os.environ[env] = "1"
+    # (by default the warp-private transforms are only taken on grids with enough rows per SM)
+    for envs in (("PDHG_FORCE_W256",), ("PDHG_NO_W256",)):
+      for env in envs:
+        os.environ[env] = "1"
       (res, errs), _ = quiet(rx.solve_HJ, ndim, n_ctrl, 1, epsl, fns, nx, ny, nt, 2.0, 2.0, T, x_arr, 70.0, nt, 0.1, nmax, 10, 1e-6, bc)
-      os.environ.pop(env)
+      for env in envs:
+        os.environ.pop(env)
       out.append((res, errs))
   finally:
     for env in ("PDHG_FORCE_PATH", "PDHG_FORCE_W256", "PDHG_NO_W256"):
