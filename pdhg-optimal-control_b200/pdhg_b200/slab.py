@@ -127,7 +127,9 @@ class DistGroup:
     for a in get(R):
       s_first, s_last = a[..., 1, :].contiguous(), a[..., R.nxl, :].contiguous()
       g_left, g_right = t.empty_like(s_first), t.empty_like(s_first)
-      ops += [dist.P2POp(dist.isend, s_first, left), dist.P2POp(dist.isend, s_last, right),
+      # (order matters when left == right, P = 2: NCCL matches the sends and receives of a peer pair in issue order, and the
+      #  left ghost has to receive the neighbour's LAST interior row)
+      ops += [dist.P2POp(dist.isend, s_last, right), dist.P2POp(dist.isend, s_first, left),
               dist.P2POp(dist.irecv, g_left, left), dist.P2POp(dist.irecv, g_right, right)]
       pend.append((a, g_left, g_right))
     if P == 1:
