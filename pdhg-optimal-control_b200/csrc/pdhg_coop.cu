@@ -23,7 +23,9 @@ namespace cg = cooperative_groups;
 
 namespace pdhg {
 
-constexpr int kNQ = 36;        // reduced quantities per epoch: 0..15 dual sweep, 16..18 primal, 20..35 second sweep of a fused pair
+constexpr int kFuseMax = 5;    // dual sweeps fused into one pass over memory (at most)
+constexpr int kNQ = 20 + 16 * (kFuseMax - 1);   // reduced quantities per epoch: 0..15 dual sweep, 16..18 primal, 20 + 16 (s - 1) + (0..15): sweep s of a fused pass
+constexpr int kNV = 36;        // the first kNV totals are handed to every thread in registers, the rest is read from shared memory on demand
 #ifndef PDHG_COOP_THREADS
 #define PDHG_COOP_THREADS 512
 #endif
@@ -60,11 +62,11 @@ struct CoopArgs {
   int has_x;          // 0 for a 1-D problem
   int sum_lo, sum_hi;        // x-rows that contribute to the error sums (slab mode: ghost rows excluded); default [0, nxe)
   int ky_off, nyh_tab;       // phase B on an exchanged ky-slab: offset and row length of the per-mode table; default 0, nyh
-  double* ext_sums;          // MODE_PHASE: device array [kNQ] receiving the grid totals of phases D / E (may be null)
+  double* ext_sums;          // MODE_PHASE: device array [kNV = 36] receiving the grid totals of phases D / E (may be null)
   int dbg_phase, dbg_pass;   // MODE_PHASE (profiling): phase id 0..3 = A,B,C,D and pass mask of phase B (bit 0,1,2)
   int d_pipe;         // 1: cp.async-pipelined dual sweep (ny even and the staging buffers fit shared memory)
   int fast_y, fast_x; // warp-private 256-point transforms along y (phases A, C) / along x (phase B)
-  int d_fuse;         // fuse two inner dual sweeps per pass while the inner loop is long (PDHG_NO_DFUSE disables)
+  int d_fuse;         // max. inner dual sweeps fused per pass while the inner loop is long (1 = off; PDHG_DFUSE=n overrides)
   double dxe, dye;
   const double* coef_xe;
   const double* coef_ye;
@@ -202,12 +204,12 @@ __device__ __forceinline__ void cta_partials(Ctx& c, const double (&vals)[N], in
   }
 }
 
-__device__ __forceinline__ void grid_gather(Ctx& c, double (&v)[kNQ]) {
+__device__ __forceinline__ void grid_gather(Ctx& c, double (&v)[kNV], int nq = kNV) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int G = gridDim.x;
   const double* part = cargs().w.partials + (size_t)(c.epoch & 1) * G * kNQ;
   c.grid.sync();
-  for (int q = warp; q < kNQ; q += nw) {
+  for (int q = warp; q < nq; q += nw) {
     double t = 0.0;
     for (int g = lane; g < G; g += 32) t += *((const volatile double*)&part[(size_t)q * G + g]);
 #pragma unroll
@@ -216,10 +218,12 @@ __device__ __forceinline__ void grid_gather(Ctx& c, double (&v)[kNQ]) {
   }
   __syncthreads();
 #pragma unroll
-  for (int q = 0; q < kNQ; ++q) v[q] = c.red()[q * kWarps];
+  for (int q = 0; q < kNV; ++q) v[q] = c.red()[q * kWarps];
   __syncthreads();
   c.epoch++;
 }
+// total of slot q >= kNV of the last gather (valid until the next cta_partials call of this CTA)
+__device__ __forceinline__ double gathered(const Ctx& c, int q) { return c.red()[q * kWarps]; }
 
 // continuity residual at one point (update_fns_in_pdhg.py:72-96).  Index 0 = the point, m/p = its -/+ neighbour.
 template <int ND>
@@ -678,6 +682,13 @@ __device__ __forceinline__ void thomas_component(double* ztd, const double* den,
   ztd = as_global(ztd); den = as_global(den); tu = as_global(tu);
   double bp = 0.0;
   int k = 0;
+  for (; k + 16 <= K; k += 16) {    // 32 independent loads ahead of the dependent chain
+    double v[16], dn[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { v[q] = ldg1(ztd + (size_t)(k + q) * modes2 + w); dn[q] = ldg1(den + (size_t)(k + q) * modes + m); }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { bp = (v[q] + ct2 * bp) * dn[q]; stg1(ztd + (size_t)(k + q) * modes2 + w, bp); }
+  }
   for (; k + 8 <= K; k += 8) {      // 16 independent loads ahead of the dependent chain
     double v[8], dn[8];
 #pragma unroll
@@ -698,6 +709,13 @@ __device__ __forceinline__ void thomas_component(double* ztd, const double* den,
   }
   double xs = bp;
   k = K - 2;
+  for (; k - 15 >= 0; k -= 16) {
+    double v[16], tv[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { v[q] = ldg1(ztd + (size_t)(k - q) * modes2 + w); tv[q] = ldg1(tu + (size_t)(k - q) * modes + m); }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { xs = v[q] - tv[q] * xs; stg1(ztd + (size_t)(k - q) * modes2 + w, xs); }
+  }
   for (; k - 7 >= 0; k -= 8) {
     double v[8], tv[8];
 #pragma unroll
@@ -962,9 +980,12 @@ __device__ __forceinline__ void dual_point(int egno, double c0, double cxm, doub
 // NS = 2 fuses two consecutive sweeps into one pass over memory: the dual update at a point needs phi_bar's stencil but only the
 // point's own rho / alp, so the second sweep runs on the first one's results while they are still in registers (same arithmetic
 // per point, same per-thread summation order => bit-identical iterates and error sums; its sums go to slots 20..35).
-template <int ND, int VW, bool HASREF, int EG, int NS = 1>
+// With NS = 2, `nx_sw` (0..kFuseMax-2) further sweeps follow in the same pass; their sums are accumulated in per-thread
+// shared-memory slots (the transform buffers are idle during this phase; same order of additions as registers would see) and
+// go to slots 36.. .
+template <int ND, int VW, bool HASREF, int EG, int NS = 1, bool XTRA = false>
 __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d, double* alp_d,
-                        const double* rho_ref, const double* alp_ref, double sigma, double epsl) {
+                        const double* rho_ref, const double* alp_ref, double sigma, double epsl, int nx_sw = 0) {
   phib = as_global(phib); rho_s = as_global(rho_s); alp_s = as_global(alp_s); rho_d = as_global(rho_d); alp_d = as_global(alp_d);
   if (HASREF) { rho_ref = as_global(rho_ref); alp_ref = as_global(alp_ref); }
   constexpr int NA = 2 * ND;
@@ -980,6 +1001,13 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
   double t_dr = 0.0, t_rr = 0.0, t_nan = 0.0, t_da[NA], t_aa[NA];      // second sweep of a fused pair (NS == 2)
 #pragma unroll
   for (int q = 0; q < NA; ++q) { s_da[q] = 0.0; s_aa[q] = 0.0; s_oa[q] = 0.0; t_da[q] = 0.0; t_aa[q] = 0.0; }
+  // sums of the extra sweeps: xacc[(sw * kAcc + q) * blockDim], q = 0 rho diff^2, 1 rho next^2, 2 NaN count, 3 + 2 t / 4 + 2 t alp t
+  constexpr int kAcc = 3 + 2 * NA;
+  double* xacc = reinterpret_cast<double*>(c.work()) + threadIdx.x;
+  const int astr = blockDim.x;
+  if (XTRA) {
+    for (int q = 0; q < nx_sw * kAcc; ++q) xacc[q * astr] = 0.0;
+  }
   // thread-linear grid-stride over VW-wide items: consecutive threads of a CTA take consecutive items of a row
   const float inv_ny2 = 1.0f / (float)ny2;
   const long long items = (long long)K * nx * ny2, istride = (long long)gridDim.x * blockDim.x;
@@ -1041,6 +1069,21 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
         rne = rn2;
 #pragma unroll
         for (int q = 0; q < NA; ++q) ane[q] = an2[q];
+#pragma unroll 1
+        for (int sw = 0; sw < (XTRA ? nx_sw : 0); ++sw) {
+          dual_point<ND>(egno, cc.e[e], (ND == 2) ? cxm.e[e] : 0.0, (ND == 2) ? cxp.e[e] : 0.0, cym, cyp, pk.e[e], rne, ane, cx,
+                         c.cy()[j + e], bx.wm, bx.wp, sigma, epsl, rc, rn2, an2);
+          if (acc_on) {
+            double* as = xacc + sw * kAcc * astr;
+            double d = rn2 - rne;
+            as[0] += d * d; as[astr] += rn2 * rn2; as[2 * astr] += is_nan(rn2) ? 1.0 : 0.0;
+#pragma unroll
+            for (int q = 0; q < NA; ++q) { d = an2[q] - ane[q]; as[(3 + 2 * q) * astr] += d * d; as[(4 + 2 * q) * astr] += an2[q] * an2[q]; }
+          }
+          rne = rn2;
+#pragma unroll
+          for (int q = 0; q < NA; ++q) ane[q] = an2[q];
+        }
       }
       rn.e[e] = rne;
 #pragma unroll
@@ -1065,6 +1108,15 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
 #pragma unroll
     for (int q = 0; q < NA; ++q) { sums[2 + 2 * q] = t_da[q]; sums[3 + 2 * q] = t_aa[q]; }
     cta_partials<16>(c, sums, 20);
+    for (int sw = 0; sw < (XTRA ? nx_sw : 0); ++sw) {
+      const double* as = xacc + sw * kAcc * astr;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) sums[q] = 0.0;
+      sums[0] = as[0]; sums[1] = as[astr]; sums[15] = as[2 * astr];
+#pragma unroll
+      for (int q = 0; q < NA; ++q) { sums[2 + 2 * q] = as[(3 + 2 * q) * astr]; sums[3 + 2 * q] = as[(4 + 2 * q) * astr]; }
+      cta_partials<16>(c, sums, 36 + 16 * sw);
+    }
   }
 }
 
@@ -1269,11 +1321,18 @@ template <int EG>
 __device__ __forceinline__ void run_D_eg(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d, double* alp_d,
                                          const double* rho_ref, const double* alp_ref, double sigma, double epsl, int ns) {
   const bool v2 = (cargs().nye & 1) == 0;
-  if (ns == 2) {        // fused pair of sweeps (callers only ask for it without reference arrays)
+  if (ns == 2) {        // fused sweeps (callers only ask for them without reference arrays)
     if (cargs().has_x) { if (v2) phase_D<2, 2, false, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
                          else phase_D<2, 1, false, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
     else { if (v2) phase_D<1, 2, false, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
            else phase_D<1, 1, false, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
+    return;
+  }
+  if (ns > 2) {
+    if (cargs().has_x) { if (v2) phase_D<2, 2, false, EG, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl, ns - 2);
+                         else phase_D<2, 1, false, EG, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl, ns - 2); }
+    else { if (v2) phase_D<1, 2, false, EG, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl, ns - 2);
+           else phase_D<1, 1, false, EG, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl, ns - 2); }
     return;
   }
   if (rho_ref) {
@@ -1364,7 +1423,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
   if (a.mode == MODE_PHASE) {
     // profiling aid: ONE phase on whatever the workspace holds (left there by a previous march), so that ncu sees each
     // phase as its own launch.  Results are not meaningful; nothing outside the workspace is written.
-    double v[kNQ];
+    double v[kNV];
     switch (a.dbg_phase) {
       case 0: run_A(c, 0, epsl); break;
       case 1: phase_B(c); break;
@@ -1378,7 +1437,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
     // grid totals of this launch's reduction (incl. the partials a preceding phase-C launch left in slots 16..18) for the
     // host: slab mode all-reduces them across ranks and takes the decisions there
     if (a.ext_sums && a.dbg_phase >= 3 && lead) {
-      for (int q = 0; q < kNQ; ++q) a.ext_sums[q] = v[q];
+      for (int q = 0; q < kNV; ++q) a.ext_sums[q] = v[q];
     }
     return;
   }
@@ -1405,7 +1464,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
     int j = 0;
     double err = 0.0;
     for (; j < p.rho_alp_iters; ++j) {
-      double v[kNQ];
+      double v[kNV];
       const int s = j & 1, d = s ^ 1;
       run_D(c, a.op_phi_in, w.rho[s], w.alp[s], w.rho[d], w.alp[d], nullptr, nullptr, a.op_step, epsl);
       grid_gather(c, v);
@@ -1453,7 +1512,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
           for (int q = 0; q < 4; ++q) if (q < A) { const double x = galp[(size_t)q * KN + g]; s6[2 + q] += x * x; }
         }
         cta_partials<6>(c, s6, 0);
-        double v[kNQ];
+        double v[kNV];
         grid_gather(c, v);    // (its grid sync also orders the copies above before phase A)
         S_row0 = v[0]; S_rho = v[1];
         for (int q = 0; q < 4; ++q) S_alp[q] = v[2 + q];
@@ -1472,7 +1531,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
         phase_B(c);
         c.grid.sync();
         TICK(1);
-        double v[kNQ];
+        double v[kNV];
         run_C(c, w.phi[cp], w.phi[cp ^ 1], w.phib, tau);
         c.grid.sync();
         TICK(2);
@@ -1486,34 +1545,50 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
         int j = 0, last = cd;
         while (j < p.rho_alp_iters) {
           const int src = last, dst = (last == f1) ? f2 : f1;
-          const bool pair = a.d_fuse && (prev_j - j >= 2) && (j + 2 <= p.rho_alp_iters);
-          run_D(c, w.phib, w.rho[src], w.alp[src], w.rho[dst], w.alp[dst], nullptr, nullptr, sigma, epsl, pair ? 2 : 1);
-          grid_gather(c, v);
+          int ns = min(min(prev_j - j, p.rho_alp_iters - j), a.d_fuse);
+          if (ns < 1) ns = 1;
+          run_D(c, w.phib, w.rho[src], w.alp[src], w.rho[dst], w.alp[dst], nullptr, nullptr, sigma, epsl, ns);
+          grid_gather(c, v, ns > 2 ? 20 + 16 * (ns - 1) : kNV);
           c.tick(9);
           if (j == 0) { e1s0 = v[16]; e1s1 = v[17]; e1nan = v[18]; }
-          double err = v[0] / v[1];
+          // exit test after each of the ns sweeps of this pass, in order (sweeps 0, 1: v[0..15], v[20..35]; 2, 3: shared memory)
+          int hit = -1;
+          {
+            double err = v[0] / v[1];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (q < A) err += v[2 + 2 * q] / v[3 + 2 * q];
-          if (!pair) {
-            last = dst; ++j;
-            if (err < p.eps) break;
-            continue;
+            for (int q = 0; q < 4; ++q) if (q < A) err += v[2 + 2 * q] / v[3 + 2 * q];
+            if (err < p.eps) hit = 0;
           }
-          if (err < p.eps) {
-            // exit after the first sweep of the pair: redo exactly that sweep (same input, same arithmetic, same sums)
-            run_D(c, w.phib, w.rho[src], w.alp[src], w.rho[dst], w.alp[dst], nullptr, nullptr, sigma, epsl, 1);
-            grid_gather(c, v);
-            last = dst; ++j;
-            break;
+          if (hit < 0 && ns >= 2) {
+            double err = v[20] / v[21];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q < A) err += v[22 + 2 * q] / v[23 + 2 * q];
+            if (err < p.eps) hit = 1;
           }
-          // second sweep of the pair: its sums sit in slots 20..35; from here on v[0..15] describe the last sweep done
+          for (int sw = 2; sw < ns && hit < 0; ++sw) {
+            const int b0 = 36 + 16 * (sw - 2);
+            double err = gathered(c, b0) / gathered(c, b0 + 1);
+            for (int q = 0; q < 4; ++q) if (q < A) err += gathered(c, b0 + 2 + 2 * q) / gathered(c, b0 + 3 + 2 * q);
+            if (err < p.eps) hit = sw;
+          }
+          int done_sw = ns;                     // sweeps of this pass that count
+          if (hit >= 0 && hit < ns - 1) {
+            // exit inside the fused pass: redo exactly hit + 1 sweeps from the same (intact) input
+            done_sw = hit + 1;
+            run_D(c, w.phib, w.rho[src], w.alp[src], w.rho[dst], w.alp[dst], nullptr, nullptr, sigma, epsl, done_sw);
+            grid_gather(c, v, done_sw > 2 ? 20 + 16 * (done_sw - 1) : kNV);
+          }
+          // v[0..15] <- sums of the last sweep done
+          if (done_sw == 2) {
 #pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = v[20 + q];
-          last = dst; j += 2;
-          err = v[0] / v[1];
+            for (int q = 0; q < 16; ++q) v[q] = v[20 + q];
+          } else if (done_sw > 2) {
+            const int b0 = 36 + 16 * (done_sw - 3);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (q < A) err += v[2 + 2 * q] / v[3 + 2 * q];
-          if (err < p.eps) break;
+            for (int q = 0; q < 16; ++q) v[q] = gathered(c, b0 + q);
+          }
+          last = dst; j += done_sw;
+          if (hit >= 0) break;
         }
         prev_j = j;
         const int nd = last;
@@ -1523,7 +1598,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
         if (multi) {
           if ((a.nye & 1) == 0) phase_E<2>(c, w.rho[nd], w.alp[nd], w.rho[cd], w.alp[cd]);
           else phase_E<1>(c, w.rho[nd], w.alp[nd], w.rho[cd], w.alp[cd]);
-          double v2[kNQ];
+          double v2[kNV];
           grid_gather(c, v2);
 #pragma unroll
           for (int q = 0; q < 5; ++q) vo[q] = v2[10 + q];
@@ -1630,7 +1705,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
 // ------------------------------------------- host side -------------------------------------------
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-struct CoopGeom { int nxe, nye, nyh, TR, TKY, grid, d_pipe, fast_y, fast_x; size_t smem; };
+struct CoopGeom { int nxe, nye, nyh, TR, TKY, grid, d_pipe, d_fuse, fast_y, fast_x; size_t smem; };
 
 static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   CoopGeom g;
@@ -1663,6 +1738,13 @@ static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   g.fast_y = (w256 && many_y && g.nye == 256 && (p.ndim == 1 ? p.bc_x == 0 : p.bc_y == 0)) ? 1 : 0;
   g.fast_x = (w256 && many_x && g.nxe == 256 && p.ndim == 2 && p.bc_x == 0) ? 1 : 0;
   if ((g.fast_y || g.fast_x) && smW > work) work = smW;
+  // fused dual sweeps: two per pass everywhere; up to kFuseMax on the large grids, whose work area already holds the
+  // per-thread accumulator slots of sweeps 3.. (3 + 4 ndim sums each)
+  g.d_fuse = (g.fast_y || g.fast_x) ? kFuseMax : 2;
+  if (const char* e = getenv("PDHG_DFUSE")) g.d_fuse = atoi(e);
+  if (g.d_fuse > kFuseMax) g.d_fuse = kFuseMax;
+  if (g.d_fuse < 1 || g.d_pipe) g.d_fuse = 1;
+  while (g.d_fuse > 2 && (size_t)(g.d_fuse - 2) * (3 + 4 * p.ndim) * kThreads * 8 > work) --g.d_fuse;
   g.smem = tab + work;
   g.grid = sm_count * kCtasPerSm;
   return g;
@@ -1726,7 +1808,7 @@ static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, 
   a.p = p;
   a.w = carve(p, ws);
   a.b = b; a.mode = mode; a.A = 2 * p.ndim;
-  a.nxe = g.nxe; a.nye = g.nye; a.nyh = g.nyh; a.TR = g.TR; a.TKY = g.TKY; a.d_pipe = g.d_pipe; a.fast_y = g.fast_y; a.fast_x = g.fast_x; a.d_fuse = (getenv("PDHG_NO_DFUSE") == nullptr && !g.d_pipe) ? 1 : 0;
+  a.nxe = g.nxe; a.nye = g.nye; a.nyh = g.nyh; a.TR = g.TR; a.TKY = g.TKY; a.d_pipe = g.d_pipe; a.fast_y = g.fast_y; a.fast_x = g.fast_x; a.d_fuse = g.d_fuse;
   a.has_x = (p.ndim == 2);
   if (p.ndim == 1) {
     a.dxe = 1.0; a.dye = p.dx; a.coef_xe = p.coef_x; a.coef_ye = p.coef_x; a.tw_xe = p.tw_x; a.tw_ye = p.tw_x;
