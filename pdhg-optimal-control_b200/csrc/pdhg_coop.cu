@@ -1740,7 +1740,9 @@ static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   if ((g.fast_y || g.fast_x) && smW > work) work = smW;
   // fused dual sweeps: two per pass everywhere; up to kFuseMax on the large grids, whose work area already holds the
   // per-thread accumulator slots of sweeps 3.. (3 + 4 ndim sums each)
-  g.d_fuse = (g.fast_y || g.fast_x) ? kFuseMax : 2;
+  // (L2-resident blocks are barrier / latency bound: a fused pass saves them nothing and a redo costs two more grid barriers)
+  const bool hbm_bound = (size_t)p.K * g.nxe * g.nye * 8 * (4 + 4 * p.ndim) > ((size_t)64 << 20);
+  g.d_fuse = !hbm_bound ? 1 : ((g.fast_y || g.fast_x) ? kFuseMax : 2);
   if (const char* e = getenv("PDHG_DFUSE")) g.d_fuse = atoi(e);
   if (g.d_fuse > kFuseMax) g.d_fuse = kFuseMax;
   if (g.d_fuse < 1 || g.d_pipe) g.d_fuse = 1;
