@@ -23,9 +23,16 @@ def is_tensor(x):
   return _torch is not None and isinstance(x, _torch.Tensor) or type(x).__module__.startswith("torch")
 
 
-def to_dev(x, device=0):
-  """numpy / torch (any device) -> contiguous fp64 CUDA tensor."""
+def current_device():
+  """The process's current CUDA device (one process per GPU: `torch.cuda.set_device(local_rank)` selects it)."""
+  return int(require_cuda().cuda.current_device())
+
+
+def to_dev(x, device=None):
+  """numpy / torch (any device) -> contiguous fp64 CUDA tensor on `device` (default: the current CUDA device)."""
   t = require_cuda()
+  if device is None:
+    device = current_device()
   if is_tensor(x):
     return x.to(device="cuda:%d" % device, dtype=t.float64).contiguous()
   return t.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).to("cuda:%d" % device)
@@ -38,6 +45,8 @@ def like_input(dev_tensor, template):
   return dev_tensor.cpu().numpy()
 
 
-def stream_ptr(device=0):
+def stream_ptr(device=None):
   t = torch()
+  if device is None:
+    device = current_device()
   return int(t.cuda.current_stream(device).cuda_stream)

@@ -17,8 +17,10 @@ _handles = {}
 
 
 def get_solver(fns_dict, nspatial, K, bc, dt, dspatial, c_on_rho, x_arr, C=1.0, pow=1.0, Ct=1.0, eps=1e-6, rho_alp_iters=10,
-               batch=1, nblocks=1, max_rec=128, device=0, path=0):
-  """Cached `pdhg_handle` for a (problem, grid, preconditioner) family."""
+               batch=1, nblocks=1, max_rec=128, device=None, path=0):
+  """Cached `pdhg_handle` for a (problem, grid, preconditioner) family on `device` (default: the current CUDA device)."""
+  if device is None:
+    device = _dev.current_device()
   ndim = fns_dict.ndim
   path = int(os.environ.get("PDHG_FORCE_PATH", path))   # testing hook: 1 single-CTA kernel, 2 cooperative kernel
   nx = int(nspatial[0])
