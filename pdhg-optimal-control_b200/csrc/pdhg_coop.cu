@@ -1069,25 +1069,47 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
         rne = rn2;
 #pragma unroll
         for (int q = 0; q < NA; ++q) ane[q] = an2[q];
-#pragma unroll 1
-        for (int sw = 0; sw < (XTRA ? nx_sw : 0); ++sw) {
-          dual_point<ND>(egno, cc.e[e], (ND == 2) ? cxm.e[e] : 0.0, (ND == 2) ? cxp.e[e] : 0.0, cym, cyp, pk.e[e], rne, ane, cx,
-                         c.cy()[j + e], bx.wm, bx.wp, sigma, epsl, rc, rn2, an2);
-          if (acc_on) {
-            double* as = xacc + sw * kAcc * astr;
-            double d = rn2 - rne;
-            as[0] += d * d; as[astr] += rn2 * rn2; as[2 * astr] += is_nan(rn2) ? 1.0 : 0.0;
-#pragma unroll
-            for (int q = 0; q < NA; ++q) { d = an2[q] - ane[q]; as[(3 + 2 * q) * astr] += d * d; as[(4 + 2 * q) * astr] += an2[q] * an2[q]; }
-          }
-          rne = rn2;
-#pragma unroll
-          for (int q = 0; q < NA; ++q) ane[q] = an2[q];
-        }
       }
       rn.e[e] = rne;
 #pragma unroll
       for (int q = 0; q < NA; ++q) an[q].e[e] = ane[q];
+    }
+    if (XTRA) {
+      // further sweeps of the fused pass: the VW points of the item advance together (independent chains for the fp64
+      // pipe), each sum is read from / written to its shared-memory slot once per item, additions in the order e = 0, 1
+#pragma unroll 1
+      for (int sw = 0; sw < nx_sw; ++sw) {
+        double rn2[VW], an2[VW][NA];
+#pragma unroll
+        for (int e = 0; e < VW; ++e) {
+          const double cym = (e == 0) ? c_l : cc.e[0], cyp = (e == VW - 1) ? c_r : cc.e[VW - 1];
+          double aoe[NA];
+#pragma unroll
+          for (int q = 0; q < NA; ++q) aoe[q] = an[q].e[e];
+          dual_point<ND>(egno, cc.e[e], (ND == 2) ? cxm.e[e] : 0.0, (ND == 2) ? cxp.e[e] : 0.0, cym, cyp, pk.e[e], rn.e[e], aoe, cx,
+                         c.cy()[j + e], bx.wm, bx.wp, sigma, epsl, rc, rn2[e], an2[e]);
+        }
+        if (acc_on) {
+          double* as = xacc + sw * kAcc * astr;
+          double s0 = as[0], s1 = as[astr], s2 = as[2 * astr];
+#pragma unroll
+          for (int e = 0; e < VW; ++e) { const double d = rn2[e] - rn.e[e]; s0 += d * d; s1 += rn2[e] * rn2[e]; s2 += is_nan(rn2[e]) ? 1.0 : 0.0; }
+          as[0] = s0; as[astr] = s1; as[2 * astr] = s2;
+#pragma unroll
+          for (int q = 0; q < NA; ++q) {
+            double sd = as[(3 + 2 * q) * astr], sa = as[(4 + 2 * q) * astr];
+#pragma unroll
+            for (int e = 0; e < VW; ++e) { const double d = an2[e][q] - an[q].e[e]; sd += d * d; sa += an2[e][q] * an2[e][q]; }
+            as[(3 + 2 * q) * astr] = sd; as[(4 + 2 * q) * astr] = sa;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < VW; ++e) {
+          rn.e[e] = rn2[e];
+#pragma unroll
+          for (int q = 0; q < NA; ++q) an[q].e[e] = an2[e][q];
+        }
+      }
     }
     stv<VW>(rho_d + g, rn);
 #pragma unroll
