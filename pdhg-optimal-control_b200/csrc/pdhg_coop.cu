@@ -204,7 +204,7 @@ __device__ __forceinline__ void cta_partials(Ctx& c, const double (&vals)[N], in
   }
 }
 
-__device__ __forceinline__ void grid_gather(Ctx& c, double (&v)[kNV], int nq = kNV) {
+__device__ __forceinline__ void grid_gather(Ctx& c, double (&v)[kNV], int nq = 20) {      // nq: slots [0, nq) are in use this epoch
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int G = gridDim.x;
   const double* part = cargs().w.partials + (size_t)(c.epoch & 1) * G * kNQ;
@@ -1570,7 +1570,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
           int ns = min(min(prev_j - j, p.rho_alp_iters - j), a.d_fuse);
           if (ns < 1) ns = 1;
           run_D(c, w.phib, w.rho[src], w.alp[src], w.rho[dst], w.alp[dst], nullptr, nullptr, sigma, epsl, ns);
-          grid_gather(c, v, ns > 2 ? 20 + 16 * (ns - 1) : kNV);
+          grid_gather(c, v, 20 + 16 * (ns - 1));
           c.tick(9);
           if (j == 0) { e1s0 = v[16]; e1s1 = v[17]; e1nan = v[18]; }
           // exit test after each of the ns sweeps of this pass, in order (sweeps 0, 1: v[0..15], v[20..35]; 2, 3: shared memory)
@@ -1598,7 +1598,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
             // exit inside the fused pass: redo exactly hit + 1 sweeps from the same (intact) input
             done_sw = hit + 1;
             run_D(c, w.phib, w.rho[src], w.alp[src], w.rho[dst], w.alp[dst], nullptr, nullptr, sigma, epsl, done_sw);
-            grid_gather(c, v, done_sw > 2 ? 20 + 16 * (done_sw - 1) : kNV);
+            grid_gather(c, v, 20 + 16 * (done_sw - 1));
           }
           // v[0..15] <- sums of the last sweep done
           if (done_sw == 2) {
