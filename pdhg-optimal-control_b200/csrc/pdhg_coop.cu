@@ -25,7 +25,7 @@ namespace pdhg {
 
 constexpr int kFuseMax = 5;    // dual sweeps fused into one pass over memory (at most)
 constexpr int kNQ = 20 + 16 * (kFuseMax - 1);   // reduced quantities per epoch: 0..15 dual sweep, 16..18 primal, 20 + 16 (s - 1) + (0..15): sweep s of a fused pass
-constexpr int kNV = 36;        // the first kNV totals are handed to every thread in registers, the rest is read from shared memory on demand
+constexpr int kNV = 20;        // the first kNV totals are handed to every thread in registers, the rest is read from shared memory on demand
 #ifndef PDHG_COOP_THREADS
 #define PDHG_COOP_THREADS 512
 #endif
@@ -62,7 +62,7 @@ struct CoopArgs {
   int has_x;          // 0 for a 1-D problem
   int sum_lo, sum_hi;        // x-rows that contribute to the error sums (slab mode: ghost rows excluded); default [0, nxe)
   int ky_off, nyh_tab;       // phase B on an exchanged ky-slab: offset and row length of the per-mode table; default 0, nyh
-  double* ext_sums;          // MODE_PHASE: device array [kNV = 36] receiving the grid totals of phases D / E (may be null)
+  double* ext_sums;          // MODE_PHASE: device array [kNV = 20] receiving the grid totals of phases D / E (may be null)
   int dbg_phase, dbg_pass;   // MODE_PHASE (profiling): phase id 0..3 = A,B,C,D and pass mask of phase B (bit 0,1,2)
   int d_pipe;         // 1: cp.async-pipelined dual sweep (ny even and the staging buffers fit shared memory)
   int fast_y, fast_x; // warp-private 256-point transforms along y (phases A, C) / along x (phase B)
@@ -1573,7 +1573,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
           grid_gather(c, v, 20 + 16 * (ns - 1));
           c.tick(9);
           if (j == 0) { e1s0 = v[16]; e1s1 = v[17]; e1nan = v[18]; }
-          // exit test after each of the ns sweeps of this pass, in order (sweeps 0, 1: v[0..15], v[20..35]; 2, 3: shared memory)
+          // exit test after each of the ns sweeps of this pass, in order (sweep 0: v[0..15]; the others: shared memory)
           int hit = -1;
           {
             double err = v[0] / v[1];
@@ -1581,14 +1581,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
             for (int q = 0; q < 4; ++q) if (q < A) err += v[2 + 2 * q] / v[3 + 2 * q];
             if (err < p.eps) hit = 0;
           }
-          if (hit < 0 && ns >= 2) {
-            double err = v[20] / v[21];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (q < A) err += v[22 + 2 * q] / v[23 + 2 * q];
-            if (err < p.eps) hit = 1;
-          }
-          for (int sw = 2; sw < ns && hit < 0; ++sw) {
-            const int b0 = 36 + 16 * (sw - 2);
+          for (int sw = 1; sw < ns && hit < 0; ++sw) {
+            const int b0 = 20 + 16 * (sw - 1);
             double err = gathered(c, b0) / gathered(c, b0 + 1);
             for (int q = 0; q < 4; ++q) if (q < A) err += gathered(c, b0 + 2 + 2 * q) / gathered(c, b0 + 3 + 2 * q);
             if (err < p.eps) hit = sw;
@@ -1601,11 +1595,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
             grid_gather(c, v, 20 + 16 * (done_sw - 1));
           }
           // v[0..15] <- sums of the last sweep done
-          if (done_sw == 2) {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = v[20 + q];
-          } else if (done_sw > 2) {
-            const int b0 = 36 + 16 * (done_sw - 3);
+          if (done_sw >= 2) {
+            const int b0 = 20 + 16 * (done_sw - 2);
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = gathered(c, b0 + q);
           }

@@ -16,7 +16,7 @@ import numpy as np
 from . import _dev, _lib
 from .set_fns import coef_tables
 
-NQ = 36      # kNQ of csrc/pdhg_coop.cu
+NQ = 20      # kNV of csrc/pdhg_coop.cu: totals handed out per launch
 
 
 class SlabRank:
