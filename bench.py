@@ -35,12 +35,15 @@ WORKLOADS = {
   "cfg3_tsp2": (1, 2, 256, 256, 65, 2, 0.0, 0.1),
   "cfg2": (1, 1, 640, 1, 161, 2, 0.1, 0.005),
   "cfg1": (1, 1, 160, 1, 41, 2, 0.0, 0.1),
+  "cfg5_tsp2": (1, 2, 2048, 2048, 257, 2, 0.1, 5e-4),
 }
 DESCR = {
   "cfg3_tsp65": "BASELINE configs[2]: egno=1 ndim=2 epsl=0 nx=ny=256 nt=65, time_step_per_PDHG=65 (one space-time block, HBM-bound)",
   "cfg3_tsp2": "BASELINE configs[2]: egno=1 ndim=2 epsl=0 nx=ny=256 nt=65, time_step_per_PDHG=2 (reference default, L2-resident block 0)",
   "cfg2": "BASELINE configs[1]: egno=1 ndim=1 epsl=0.1 nx=640 nt=161 tsp=2 at the stable stepsz_param=0.005 (block 0)",
   "cfg1": "BASELINE configs[0]: egno=1 ndim=1 epsl=0 nx=160 nt=41 tsp=2 stepsz_param=0.1 (block 0)",
+  "cfg5_tsp2": "BASELINE configs[4] grid on ONE GPU: egno=1 ndim=2 epsl=0.1 nx=ny=2048 nt=257 tsp=2, stepsz_param=5e-4 (block 0, fixed "
+               "iteration budget; generic 2048-point transforms; the x-slab decomposition is scripts/slab_bench.py)",
 }
 
 
@@ -398,7 +401,7 @@ def main():
     line["cpu_baseline"] = cpu_baseline(pb)
     if not a.no_others:
       others = {}
-      for nm, its in (("cfg3_tsp2", 2000), ("cfg2", 20000), ("cfg1", 3000)):
+      for nm, its in (("cfg3_tsp2", 2000), ("cfg2", 20000), ("cfg1", 3000), ("cfg5_tsp2", 100)):
         if nm != a.workload:
           try:
             others[nm] = secondary(nm, local, its)

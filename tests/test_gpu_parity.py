@@ -225,6 +225,23 @@ def test_warp_private_256_point_transforms_vs_oracle(pk, ndim, nx, ny, nt, epsl,
     assert relmax(a, b) < 1e-12
 
 
+@pytest.mark.parametrize("nx,ny", [(2048, 8), (8, 2048), (512, 24)])
+def test_long_transform_axes_vs_oracle(pk, nx, ny):
+  """BASELINE configs[4] axis length (2048 = 16 * 16 * 8 points, three Stockham stages) along x and along y, viscous, tiny step
+  size as SURVEY.md section 8(d) prescribes for that grid: first iterations against the oracle."""
+  from oracle import pdhg_numpy as orc
+  rx = pk["rx"]
+  n_ctrl, bc, _ = rx.problem_setup(1, 2)
+  x_arr = rx.make_x_arr(2, nx, ny, 2.0, 2.0)
+  fns, _ = quiet(pk["sf"].set_up_example_fns, 1, 2, 0)
+  (res, errs), _ = quiet(rx.solve_HJ, 2, n_ctrl, 1, 0.1, fns, nx, ny, 2, 2.0, 2.0, 1.0 / 256, x_arr, 70.0, 2, 5e-4, 12, 10, 1e-6, bc)
+  res_o, errs_o = orc.solve_HJ(2, n_ctrl, 1, 0.1, orc.set_up_example_fns(1, 2, 0), nx, ny, 2, 2.0, 2.0, 1.0 / 256, x_arr, 70.0, 2, 5e-4, 12, 10,
+                               1e-6, bc)
+  for a, b in zip(res[0][1:], res_o[0][1:]):
+    assert relmax(a, b) < TOL
+  assert relmax(errs[0], errs_o[0]) < 1e-7
+
+
 def test_spacetime_block_2d_vs_oracle(pk):
   """time_step_per_PDHG = nt (one space-time block, the HBM-bound regime): FFT-xy + Thomas-t over K = 8 rows."""
   from oracle import pdhg_numpy as orc
