@@ -111,10 +111,12 @@ int pdhg_phase_times(pdhg_handle* h, double* out16);
  *   phase 1 = B: zt in place                   x-FFT, per-mode solve, inverse x-FFT; `nyh_override`/`ky_off`/`nyh_tab` select the
  *                                              ky-slab this rank owns after the transpose (table row length nyh_tab)
  *   phase 2 = C: (zt, phi_in) -> phi_out, phib inverse y-FFT + phi update (step = tau)
- *   phase 3 = D: (phib, rho_in, alp_in) -> rho_out, alp_out   one dual sweep (step = sigma); may run in place
+ *   phase 3 = D: (phib, rho_in, alp_in) -> rho_out, alp_out   one dual sweep (step = sigma), may run in place; `pass_mask` = 2 fuses two
+ *                                              consecutive sweeps into the pass (not in place; the second sweep's sums go to slots 20..35)
  *   phase 4 = E: outer differences of (rho_out, alp_out) against (rho_in, alp_in)
  * Rows outside [sum_lo, sum_hi) (ghost rows) do not contribute to the error sums.  Phases 3 and 4 store the grid totals of the
- * 20 reduced quantities (dual sums in 0..15, the preceding phase C's primal sums in 16..18) to bufs->sums (device). */
+ * reduced quantities (dual sums in 0..15, the preceding phase C's primal sums in 16..18, a fused second sweep in 20..35) to
+ * bufs->sums (device, room for 36 doubles). */
 typedef struct pdhg_ext_buffers {
   double *phi_in, *phi_out, *phib, *rho_in, *alp_in, *rho_out, *alp_out;
   void* zt;

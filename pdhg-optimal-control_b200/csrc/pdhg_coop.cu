@@ -1450,7 +1450,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
       case 0: run_A(c, 0, epsl); break;
       case 1: phase_B(c); break;
       case 2: run_C(c, w.phi[0], w.phi[1], w.phib, a.op_step); break;
-      case 3: run_D(c, w.phib, w.rho[0], w.alp[0], w.rho[1], w.alp[1], nullptr, nullptr, a.op_step, epsl); grid_gather(c, v); break;
+      case 3: {
+        // dbg_pass = number of sweeps to fuse in this pass (slab mode; 2 needs no shared memory, more only up to d_fuse)
+        const int ns = (a.dbg_pass == 2 || (a.dbg_pass >= 3 && a.dbg_pass <= a.d_fuse)) ? a.dbg_pass : 1;
+        run_D(c, w.phib, w.rho[0], w.alp[0], w.rho[1], w.alp[1], nullptr, nullptr, a.op_step, epsl, ns);
+        grid_gather(c, v, 20 + 16 * (ns - 1));
+        if (a.ext_sums && lead) {
+          for (int q = kNV; q < 20 + 16 * (ns - 1); ++q) a.ext_sums[q] = gathered(c, q);
+        }
+        break;
+      }
       default:
         if ((a.nye & 1) == 0) phase_E<2>(c, w.rho[1], w.alp[1], w.rho[0], w.alp[0]); else phase_E<1>(c, w.rho[1], w.alp[1], w.rho[0], w.alp[0]);
         grid_gather(c, v);

@@ -16,7 +16,8 @@ import numpy as np
 from . import _dev, _lib
 from .set_fns import coef_tables
 
-NQ = 20      # kNV of csrc/pdhg_coop.cu: totals handed out per launch
+NQ = 36      # totals a phase launch hands out: 0..15 dual sweep, 16..18 primal, 20..35 second sweep of a fused pair
+FUSE = 2     # dual sweeps per pass while the inner loop is long (as the single-GPU kernel does; 2 needs no extra buffers)
 
 
 class SlabRank:
@@ -49,8 +50,8 @@ class SlabRank:
     z = lambda *sh: t.zeros(sh, dtype=f64, device=self.dev)
     self.phi = [z(2, self.nxp, ny), z(2, self.nxp, ny)]
     self.phib = z(2, self.nxp, ny)
-    self.rho = [z(1, self.nxp, ny), z(1, self.nxp, ny)]
-    self.alp = [z(4, 1, self.nxp, ny), z(4, 1, self.nxp, ny)]
+    self.rho = [z(1, self.nxp, ny) for _ in range(3)]        # the outer iterate + two work buffers of the inner dual loop
+    self.alp = [z(4, 1, self.nxp, ny) for _ in range(3)]
     self.zt = t.zeros((1, self.nyh, self.nxp), dtype=c128, device=self.dev)
     self.ztB = t.zeros((1, max(self.kyl, 1), nx), dtype=c128, device=self.dev)
     self.sums = z(NQ)
@@ -60,8 +61,9 @@ class SlabRank:
     return a[..., 1:self.nxl + 1, :]
 
   def ext(self, h, phase, step, epsl, **kw):
-    ptr = {k: (v.data_ptr() if v is not None else None) for k, v in kw.items() if k not in ("nyh_override", "ky_off", "nyh_tab")}
-    extra = {k: v for k, v in kw.items() if k in ("nyh_override", "ky_off", "nyh_tab")}
+    scalars = ("nyh_override", "ky_off", "nyh_tab", "pass_mask")
+    ptr = {k: (v.data_ptr() if v is not None else None) for k, v in kw.items() if k not in scalars}
+    extra = {k: v for k, v in kw.items() if k in scalars}
     h.ext_phase(phase, step, epsl, 1, self.nxl + 1, stream=_dev.stream_ptr(self.dev.index), **extra, **ptr)
 
 
@@ -205,6 +207,7 @@ def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_ite
   tot = group.allreduce(loc)[0].cpu().numpy()
   S_row0, S_rho, S_alp = tot[0], tot[1], tot[2:6].copy()
   n_inner, reason, err1, err2 = 0, _lib.END_MAXITER, float("nan"), float("nan")
+  prev_j = rho_alp_iters
   it = 0
   for it in range(n_maxiter):
     group.halo(lambda R: [R.rho[R.cd], R.alp[R.cd][0], R.alp[R.cd][1]])
@@ -219,26 +222,50 @@ def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_ite
       # phase C of the local handle normalises the inverse transforms by 1 / (nxp ny); the x-transform ran over the global nx
       R.ext(R.hL, 2, tau * R.nxp / R.nx, epsl, zt=R.zt, phi_in=R.phi[R.cp], phi_out=R.phi[R.cp ^ 1], phib=R.phib)
     group.halo(lambda R: [R.phib])
-    j = 0
+    # inner dual loop, as in the single-GPU kernel: buffer cd stays intact, the passes ping-pong between the other two; while
+    # the previous outer iteration needed several sweeps two sweeps are fused per pass (one launch, one all-reduce), and an
+    # exit after the first sweep of a pair is handled by redoing exactly that sweep from the pair's input
+    cd = ranks[0].cd
+    f1, f2 = (cd + 1) % 3, (cd + 2) % 3
+    j, last = 0, cd
+
+    def inner_err(v, b0):
+      with np.errstate(all="ignore"):
+        return v[b0] / v[b0 + 1] + sum(v[b0 + 2 + 2 * q] / v[b0 + 3 + 2 * q] for q in range(4))
+
     while j < rho_alp_iters:
+      src, dst = last, (f2 if last == f1 else f1)
+      ns = max(1, min(prev_j - j, rho_alp_iters - j, FUSE))
       for R in ranks:
-        nd = R.cd ^ 1
-        src_r, src_a = (R.rho[R.cd], R.alp[R.cd]) if j == 0 else (R.rho[nd], R.alp[nd])
-        R.ext(R.hL, 3, sigma, epsl, phib=R.phib, rho_in=src_r, alp_in=src_a, rho_out=R.rho[nd], alp_out=R.alp[nd], sums=R.sums)
+        R.ext(R.hL, 3, sigma, epsl, pass_mask=ns, phib=R.phib, rho_in=R.rho[src], alp_in=R.alp[src], rho_out=R.rho[dst], alp_out=R.alp[dst],
+              sums=R.sums)
       v = group.allreduce_sums()
       if j == 0:
         e1s0, e1s1, e1nan = v[16], v[17], v[18]
-      j += 1
-      with np.errstate(all="ignore"):
-        err = v[0] / v[1] + sum(v[2 + 2 * q] / v[3 + 2 * q] for q in range(4))
-      if err < eps:
+      hit = -1
+      for sw in range(ns):
+        if inner_err(v, 0 if sw == 0 else 20 + 16 * (sw - 1)) < eps:
+          hit = sw
+          break
+      done = ns
+      if 0 <= hit < ns - 1:
+        done = hit + 1
+        for R in ranks:
+          R.ext(R.hL, 3, sigma, epsl, pass_mask=done, phib=R.phib, rho_in=R.rho[src], alp_in=R.alp[src], rho_out=R.rho[dst],
+                alp_out=R.alp[dst], sums=R.sums)
+        v = group.allreduce_sums()
+      if done > 1:
+        v = v.copy()
+        v[:16] = v[20 + 16 * (done - 2):36 + 16 * (done - 2)]
+      last, j = dst, j + done
+      if hit >= 0:
         break
+    prev_j = j
     n_inner += j
     d_rho, d_alp = v[0], [v[2 + 2 * q] for q in range(4)]
     if j > 1:
       for R in ranks:
-        nd = R.cd ^ 1
-        R.ext(R.hL, 4, 0.0, epsl, rho_in=R.rho[R.cd], alp_in=R.alp[R.cd], rho_out=R.rho[nd], alp_out=R.alp[nd], sums=R.sums)
+        R.ext(R.hL, 4, 0.0, epsl, rho_in=R.rho[cd], alp_in=R.alp[cd], rho_out=R.rho[last], alp_out=R.alp[last], sums=R.sums)
       vo = group.allreduce_sums()
       d_rho, d_alp = vo[10], [vo[11 + q] for q in range(4)]
     with np.errstate(all="ignore"):
@@ -253,7 +280,7 @@ def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_ite
     S_rho, S_alp = v[1], np.array([v[3 + 2 * q] for q in range(4)])
     for R in ranks:
       R.cp ^= 1
-      R.cd ^= 1
+      R.cd = last
     if err1 < eps and err2 < eps:
       reason = _lib.END_CONVERGED
       break
