@@ -49,7 +49,7 @@ enum pdhg_inst_status {
   PDHG_INST_OK = 0,
   PDHG_INST_SOL_NAN = 1,      /* step-size fallback exhausted: "algorithm failed" (utils_pdhg_solver.py:184-187) */
   PDHG_INST_PAUSED = 3,       /* stopped at iter_pause; resume with iter_begin = iters */
-  PDHG_INST_LOG_OVERFLOW = 4  /* more than max_rec-1 periodic records in one block; extra rows dropped */
+  PDHG_INST_LOG_OVERFLOW = 4  /* more than max_rec-1 periodic records in some block: the extra rows were dropped, the march itself ran to its end */
 };
 
 /* how a time block ended (pdhg_logs.end_reason) */
@@ -160,6 +160,23 @@ int pdhg_solve_block(pdhg_handle* h, const double* phi0_dev, const double* rho0_
 int pdhg_multi_step(pdhg_handle* h, const double* g_dev, const double* epsl_host, const double* stepsz_host,
                     int64_t n_maxiter, int32_t print_freq, double* phi_all_dev, double* rho_all_dev,
                     double* alp_all_dev, pdhg_logs* logs, void* stream);
+
+/* pdhg_multi_step restricted to the time blocks [blk_begin, blk_end) of the march (utils_pdhg_solver.py:165-213, one pass of
+ * the `for i in range(init_t_ind, nt_PDHG)` loop per block): what the host needs to write the reference's `save_middle` file
+ * after EVERY block (:211-212) and to resume a march (`load_middle`, :139-154 — unwired and broken in the reference).
+ * blk_begin = 0 starts from g like pdhg_multi_step; blk_begin > 0 continues from the handle's marching state — the next
+ * block's warm-started phi0 and (rho0, alp0), left there by the previous range call or installed with pdhg_set_march_state —
+ * with the CURRENT step size stepsz_cur_host[b] (NULL: the initial one).  The fallback decrement and floor always derive from
+ * stepsz_host[b], the initial stepsz_param (:160-161).  Outputs land in rows [blk_begin K, blk_end K) of the *_all arrays; logs
+ * are [B][nblocks] as in pdhg_multi_step (entries outside the range keep earlier values). */
+int pdhg_multi_step_range(pdhg_handle* h, const double* g_dev, const double* epsl_host, const double* stepsz_host,
+                          const double* stepsz_cur_host, int64_t n_maxiter, int32_t print_freq, int32_t blk_begin,
+                          int32_t blk_end, double* phi_all_dev, double* rho_all_dev, double* alp_all_dev, pdhg_logs* logs,
+                          void* stream);
+/* marching state between two time blocks (device buffers, reference layouts): phi0 [B][K+1][n] of the NEXT block (already
+ * shifted by phi_curr[-1] - phi0[0], utils_pdhg_solver.py:200-203), rho0 [B][K][n], alp0 [B][2 ndim][K][n][n_ctrl] */
+int pdhg_get_march_state(pdhg_handle* h, double* phi0_dev, double* rho0_dev, double* alp0_dev, void* stream);
+int pdhg_set_march_state(pdhg_handle* h, const double* phi0_dev, const double* rho0_dev, const double* alp0_dev, void* stream);
 
 /* Same as pdhg_multi_step with HOST buffers for g and the three outputs (H2D / D2H copies inside). */
 int pdhg_multi_step_host(pdhg_handle* h, const double* g_host, const double* epsl_host, const double* stepsz_host,

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256, 2) pdhg1d_cta_kernel(const MarchParams p)
   const int nt_all = p.nblocks * K + 1;
 
   int status = ST_OK;
+  bool log_overflow = false;     // sticky: more periodic records than max_rec - 1 in some block (rows dropped, march goes on)
   int blocks_done = p.blk_begin;
   long long inner_total = 0;
   // diagnostic cycle counters (instance 0, thread 0): residual, FFT, solve, IFFT, phi update, dual sweeps, decisions
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(256, 2) pdhg1d_cta_kernel(const MarchParams p)
         p.nrec[lb] = nrec;
         p.end_reason[lb] = reason;
       }
-      if (logfull) status = ST_LOG_OVERFLOW;
+      log_overflow = log_overflow || logfull;
       if (reason == END_PAUSED) status = ST_PAUSED;
       __syncthreads();
       if (p.handoff && reason != END_PAUSED) {
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(256, 2) pdhg1d_cta_kernel(const MarchParams p)
   if (prof) for (int q = 0; q < 8; ++q) p.dbg_ns[q] = (double)tc[q];
 #undef TCK
   if (tid == 0) {
-    p.status[b] = status;
+    p.status[b] = (status == ST_OK && log_overflow) ? ST_LOG_OVERFLOW : status;   // overflow never stops the march (only NaN failure and pause do)
     p.blocks_done[b] = blocks_done;
     p.stepsz[b] = stepsz;
     p.inner_total[b] = inner_total;

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(512, 1) pdhg1d_k1_kernel(const MarchParams p) 
   }
 
   int status = ST_OK;
+  bool log_overflow = false;     // sticky: more periodic records than max_rec - 1 in some block (rows dropped, march goes on)
   int blocks_done = p.blk_begin;
   long long inner_total = 0;
 
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(512, 1) pdhg1d_k1_kernel(const MarchParams p) 
         break;
       }
       if (tid == 0) { p.iters[lb] = iters_done; p.stepsz_used[lb] = stepsz; p.nrec[lb] = nrec; p.end_reason[lb] = reason; }
-      if (logfull) status = ST_LOG_OVERFLOW;
+      log_overflow = log_overflow || logfull;
       if (reason == END_PAUSED) status = ST_PAUSED;
       if (p.handoff && reason != END_PAUSED) {
         double* pa = p.phi_all + ((size_t)b * nt_all + (size_t)blk) * nx;
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(512, 1) pdhg1d_k1_kernel(const MarchParams p) 
     }
   }
   if (tid == 0) {
-    p.status[b] = status;
+    p.status[b] = (status == ST_OK && log_overflow) ? ST_LOG_OVERFLOW : status;   // overflow never stops the march (only NaN failure and pause do)
     p.blocks_done[b] = blocks_done;
     p.stepsz[b] = stepsz;
     p.inner_total[b] = inner_total;

@@ -36,6 +36,18 @@ using namespace pdhg;
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
+// Every entry point runs on the handle's device and restores the caller's current device on every exit path.
+struct DeviceGuard {
+  int prev = -1;
+  bool good = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) good = (cudaSetDevice(dev) == cudaSuccess); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  bool ok() const { return good; }
+};
+
 #define CU(call)                                                                                   \
   do {                                                                                             \
     cudaError_t e_ = (call);                                                                       \
@@ -70,6 +82,8 @@ struct pdhg_handle {
   double* dbg_ns = nullptr;
   double ext_epsl = 0.0;
   bool ext_epsl_set = false;
+  Knobs knobs{};              // diagnostic environment knobs, read once in pdhg_create
+  int max_radix = 16;
   void* ws = nullptr;         // cooperative-kernel workspace
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the solver kernel(s) of the last march on its stream
   bool ev_valid = false;
@@ -90,7 +104,6 @@ static cudaError_t dalloc(pdhg_handle* h, T** p, size_t count) {
 }
 
 static bool make_plan(int n, FftPlan* plan, int max_radix = 16) {
-  if (const char* e = getenv("PDHG_MAX_RADIX")) { const int m_ = atoi(e); if (m_ < max_radix) max_radix = m_; }
   plan->n = n;
   plan->nstages = 0;
   int m = n;
@@ -135,7 +148,7 @@ extern "C" const char* pdhg_last_error(void) { return g_err.c_str(); }
 
 extern "C" void pdhg_destroy(pdhg_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (void* p : h->owned) cudaFree(p);
@@ -152,19 +165,20 @@ extern "C" double pdhg_last_kernel_ms(const pdhg_handle* h) {
 extern "C" int64_t pdhg_launch_count(const pdhg_handle* h) { return h ? h->launches : 0; }
 
 static void fill_params(pdhg_handle* h, MarchParams* p);
-static int upload_scalars(pdhg_handle* h, const double* epsl_host, const double* stepsz_host, cudaStream_t s);
+static int upload_scalars(pdhg_handle* h, const double* epsl_host, const double* stepsz_host, cudaStream_t s, const double* stepsz_cur_host = nullptr);
 
 extern "C" int pdhg_phase_times(pdhg_handle* h, double* out6 /* 16 doubles */) {
   if (!h || !out6) return fail(PDHG_ERR_ARG, "pdhg_phase_times: null argument");
   if (h->path != 2) {
     // single-CTA kernel: clock cycles of instance 0 per sub-step (only when PDHG_PROFILE is set)
-    CU(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     CU(cudaMemcpy(out6, h->dbg_ns, 16 * sizeof(double), cudaMemcpyDeviceToHost));
     return PDHG_OK;
   }
   MarchParams p;
   fill_params(h, &p);
-  CU(cudaSetDevice(h->cfg.device));
+  DeviceGuard guard(h->cfg.device);
+  if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
   CU(coop_phase_times(p, h->ws, out6));
   return PDHG_OK;
 }
@@ -172,8 +186,10 @@ extern "C" int pdhg_phase_times(pdhg_handle* h, double* out6 /* 16 doubles */) {
 extern "C" int pdhg_ext_phase(pdhg_handle* h, int phase, int pass_mask, double step, double epsl, const pdhg_ext_buffers* bufs,
                               int sum_lo, int sum_hi, int nyh_override, int ky_off, int nyh_tab, void* stream) {
   if (!h || !bufs || phase < 0 || phase > 4) return fail(PDHG_ERR_ARG, "pdhg_ext_phase: bad argument");
+  if (h->B != 1) return fail(PDHG_ERR_ARG, "pdhg_ext_phase: slab mode needs a handle with batch = 1");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  CU(cudaSetDevice(h->cfg.device));
+  DeviceGuard guard(h->cfg.device);
+  if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
   if (h->ext_epsl != epsl || !h->ext_epsl_set) {
     int rc = upload_scalars(h, &epsl, nullptr, s);
     if (rc) return rc;
@@ -192,7 +208,8 @@ extern "C" int pdhg_ext_phase(pdhg_handle* h, int phase, int pass_mask, double s
 
 extern "C" int pdhg_debug_phase(pdhg_handle* h, int phase, int pass_mask, double step, int reps) {
   if (!h || phase < 0 || phase > 3 || reps < 1) return fail(PDHG_ERR_ARG, "pdhg_debug_phase: bad argument");
-  CU(cudaSetDevice(h->cfg.device));
+  DeviceGuard guard(h->cfg.device);
+  if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
   MarchParams p;
   fill_params(h, &p);
   for (int r = 0; r < reps; ++r) { CU(launch_debug_phase(p, h->ws, phase, pass_mask, step, nullptr)); h->launches += 1; }
@@ -218,7 +235,8 @@ extern "C" int pdhg_create(const pdhg_config* cfg, const double* coef_x, const d
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || c.device >= ndev)
     return fail(PDHG_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
-  CU(cudaSetDevice(c.device));
+  DeviceGuard guard(c.device);
+  if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
 
   pdhg_handle* h = new pdhg_handle();
   h->cfg = c;
@@ -226,12 +244,23 @@ extern "C" int pdhg_create(const pdhg_config* cfg, const double* coef_x, const d
   h->n = (size_t)c.nx * c.ny;
   h->B = c.batch;
   h->nyh = (c.ndim == 2) ? c.ny / 2 + 1 : 1;
-  if (!make_plan(c.nx, &h->plan_x) || (c.ndim == 2 && !make_plan(c.ny, &h->plan_y))) {
+  {
+    auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    h->knobs.no_w256 = getenv("PDHG_NO_W256") != nullptr;
+    h->knobs.force_w256 = getenv("PDHG_FORCE_W256") != nullptr;
+    h->knobs.dfuse = env_int("PDHG_DFUSE", 0);
+    h->knobs.tma = env_int("PDHG_TMA", -1);
+    h->knobs.no_k1 = getenv("PDHG_NO_K1") != nullptr;
+    h->knobs.profile = getenv("PDHG_PROFILE") != nullptr;
+    h->max_radix = env_int("PDHG_MAX_RADIX", 16);
+    if (h->max_radix > 16 || h->max_radix < 2) h->max_radix = 16;
+  }
+  if (!make_plan(c.nx, &h->plan_x, h->max_radix) || (c.ndim == 2 && !make_plan(c.ny, &h->plan_y, h->max_radix))) {
     delete h;
     return fail(PDHG_ERR_UNSUPPORTED, "grid size has too many prime factors for the FFT plan");
   }
   if (c.ndim == 1) { h->plan_y.n = 1; h->plan_y.nstages = 0; }
-  make_plan(c.nx, &h->plan_1d, 8);
+  make_plan(c.nx, &h->plan_1d, h->max_radix < 8 ? h->max_radix : 8);
   // path selection
   int dev_smem = 0;
   cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device);
@@ -346,18 +375,20 @@ static void fill_params(pdhg_handle* h, MarchParams* p) {
   p->plan_x = h->plan_x; p->plan_y = h->plan_y; p->plan_1d = h->plan_1d;
   p->st_phi = h->st_phi; p->st_rho = h->st_rho; p->st_alp = h->st_alp;
   p->iters = h->iters; p->stepsz_used = h->stepsz_used; p->nrec = h->nrec; p->errlog = h->errlog;
-  p->dbg_ns = getenv("PDHG_PROFILE") ? h->dbg_ns : nullptr;
+  p->knobs = h->knobs;
+  p->dbg_ns = h->knobs.profile ? h->dbg_ns : nullptr;
   p->end_reason = h->end_reason; p->status = h->status; p->blocks_done = h->blocks_done; p->inner_total = h->inner_total;
 }
 
-static int upload_scalars(pdhg_handle* h, const double* epsl_host, const double* stepsz_host, cudaStream_t s) {
+static int upload_scalars(pdhg_handle* h, const double* epsl_host, const double* stepsz_host, cudaStream_t s, const double* stepsz_cur_host) {
   const int B = h->B;
   std::vector<double> e(B), st(B), dl(B), fl(B);
   for (int b = 0; b < B; ++b) {
     e[b] = epsl_host ? epsl_host[b] : 0.0;
-    st[b] = stepsz_host ? stepsz_host[b] : 0.0;
-    const double mn = st[b] / 10;          // stepsz_param_min  (utils_pdhg_solver.py:160)
-    dl[b] = st[b] / 10;                    // stepsz_param_delta (:161)
+    const double st0 = stepsz_host ? stepsz_host[b] : 0.0;     // the initial stepsz_param: decrement and floor derive from it
+    st[b] = stepsz_cur_host ? stepsz_cur_host[b] : st0;        // the step size this launch starts with (resume: after earlier fallbacks)
+    const double mn = st0 / 10;            // stepsz_param_min  (utils_pdhg_solver.py:160)
+    dl[b] = st0 / 10;                      // stepsz_param_delta (:161)
     fl[b] = mn + dl[b];                    // threshold of :181
   }
   CU(cudaMemcpyAsync(h->epsl, e.data(), B * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -389,7 +420,7 @@ static int run_march(pdhg_handle* h, const MarchParams& p, cudaStream_t s) {
   CU(cudaEventRecord(h->ev0, s));
   struct Rec { pdhg_handle* h; cudaStream_t s; ~Rec() { h->ev_valid = (cudaEventRecord(h->ev1, s) == cudaSuccess); } } rec{h, s};
   if (h->path == 1) {
-    if (h->green_R >= 0 && getenv("PDHG_NO_K1") == nullptr) CU(launch_pdhg1d_k1(p, h->B, s));   // K = 1 register-resident kernel
+    if (h->green_R >= 0 && !h->knobs.no_k1) CU(launch_pdhg1d_k1(p, h->B, s));   // K = 1 register-resident kernel
     else CU(launch_pdhg1d_cta(p, h->B, s));
     h->launches += 1;
   } else {
@@ -429,7 +460,8 @@ extern "C" int pdhg_solve_block(pdhg_handle* h, const double* phi0, const double
     return fail(PDHG_ERR_ARG, "pdhg_solve_block: null argument");
   if (n_maxiter < 1 || iter_begin < 0 || iter_begin >= n_maxiter) return fail(PDHG_ERR_ARG, "pdhg_solve_block: bad iteration range");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  CU(cudaSetDevice(h->cfg.device));
+  DeviceGuard guard(h->cfg.device);
+  if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
   const pdhg_config& c = h->cfg;
   const size_t B = h->B, kn = (size_t)c.K * h->n, np = (size_t)(c.K + 1) * h->n;
   int rc = upload_scalars(h, epsl_host, stepsz_host, s);
@@ -455,14 +487,15 @@ extern "C" int pdhg_solve_block(pdhg_handle* h, const double* phi0, const double
 
 static int multi_step_impl(pdhg_handle* h, const double* g_dev, const double* epsl_host, const double* stepsz_host,
                            int64_t n_maxiter, int32_t print_freq, double* phi_all, double* rho_all, double* alp_all,
-                           pdhg_logs* logs, cudaStream_t s) {
+                           pdhg_logs* logs, cudaStream_t s, int blk_begin = 0, int blk_end = -1, const double* stepsz_cur_host = nullptr) {
   const pdhg_config& c = h->cfg;
-  int rc = upload_scalars(h, epsl_host, stepsz_host, s);
+  if (blk_end < 0) blk_end = c.nblocks;
+  int rc = upload_scalars(h, epsl_host, stepsz_host, s, stepsz_cur_host);
   if (rc) return rc;
   MarchParams p;
   fill_params(h, &p);
   p.n_maxiter = n_maxiter; p.iter_begin = 0; p.iter_pause = n_maxiter; p.print_freq = print_freq;
-  p.nblocks = c.nblocks; p.blk_begin = 0; p.blk_end = c.nblocks; p.handoff = 1; p.fallback = 1;
+  p.nblocks = c.nblocks; p.blk_begin = blk_begin; p.blk_end = blk_end; p.handoff = 1; p.fallback = 1;
   p.phi_all = phi_all; p.rho_all = rho_all;
   const size_t kn_all = (size_t)c.nblocks * c.K * h->n;
   if (c.n_ctrl == 1) {
@@ -471,8 +504,10 @@ static int multi_step_impl(pdhg_handle* h, const double* g_dev, const double* ep
     if (!h->alp_all_planar) CU(dalloc(h, &h->alp_all_planar, (size_t)h->B * h->A * kn_all));
     p.alp_all = h->alp_all_planar;
   }
-  CU(launch_init_state(p, g_dev, h->B, s));
-  h->launches += 1;
+  if (blk_begin == 0) {      // phi0 = tile(g), rho0 = c_on_rho, alp0 = 0 (utils_pdhg_solver.py:123-137); later ranges continue from the handle's state
+    CU(launch_init_state(p, g_dev, h->B, s));
+    h->launches += 1;
+  }
   rc = run_march(h, p, s);
   if (rc) return rc;
   if (c.n_ctrl != 1) {
@@ -482,12 +517,50 @@ static int multi_step_impl(pdhg_handle* h, const double* g_dev, const double* ep
   return download_logs(h, c.nblocks, logs, s);
 }
 
+extern "C" int pdhg_multi_step_range(pdhg_handle* h, const double* g_dev, const double* epsl_host, const double* stepsz_host,
+                                     const double* stepsz_cur_host, int64_t n_maxiter, int32_t print_freq, int32_t blk_begin,
+                                     int32_t blk_end, double* phi_all, double* rho_all, double* alp_all, pdhg_logs* logs, void* stream) {
+  if (!h || !stepsz_host || !phi_all || !rho_all || !alp_all) return fail(PDHG_ERR_ARG, "pdhg_multi_step_range: null argument");
+  if (n_maxiter < 1) return fail(PDHG_ERR_ARG, "pdhg_multi_step_range: n_maxiter must be >= 1");
+  if (blk_begin < 0 || blk_end > h->cfg.nblocks || blk_begin >= blk_end) return fail(PDHG_ERR_ARG, "pdhg_multi_step_range: bad block range");
+  if (blk_begin == 0 && !g_dev) return fail(PDHG_ERR_ARG, "pdhg_multi_step_range: g is required when the range starts at block 0");
+  DeviceGuard guard(h->cfg.device);
+  if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
+  return multi_step_impl(h, g_dev, epsl_host, stepsz_host, n_maxiter, print_freq, phi_all, rho_all, alp_all, logs,
+                         static_cast<cudaStream_t>(stream), blk_begin, blk_end, stepsz_cur_host);
+}
+
+// marching state between time blocks: phi0 of the next block (already warm-started, utils_pdhg_solver.py:200-203), rho0, alp0
+extern "C" int pdhg_get_march_state(pdhg_handle* h, double* phi0, double* rho0, double* alp0, void* stream) {
+  if (!h || !phi0 || !rho0 || !alp0) return fail(PDHG_ERR_ARG, "pdhg_get_march_state: null argument");
+  DeviceGuard guard(h->cfg.device);
+  if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const pdhg_config& c = h->cfg;
+  const size_t B = h->B, kn = (size_t)c.K * h->n, np = (size_t)(c.K + 1) * h->n;
+  CU(cudaMemcpyAsync(phi0, h->st_phi, B * np * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(rho0, h->st_rho, B * kn * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  return alp_from_planar(h, h->st_alp, alp0, kn, s);
+}
+extern "C" int pdhg_set_march_state(pdhg_handle* h, const double* phi0, const double* rho0, const double* alp0, void* stream) {
+  if (!h || !phi0 || !rho0 || !alp0) return fail(PDHG_ERR_ARG, "pdhg_set_march_state: null argument");
+  DeviceGuard guard(h->cfg.device);
+  if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const pdhg_config& c = h->cfg;
+  const size_t B = h->B, kn = (size_t)c.K * h->n, np = (size_t)(c.K + 1) * h->n;
+  CU(cudaMemcpyAsync(h->st_phi, phi0, B * np * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(h->st_rho, rho0, B * kn * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  return alp_to_planar(h, alp0, h->st_alp, s);
+}
+
 extern "C" int pdhg_multi_step(pdhg_handle* h, const double* g_dev, const double* epsl_host, const double* stepsz_host,
                                int64_t n_maxiter, int32_t print_freq, double* phi_all, double* rho_all, double* alp_all,
                                pdhg_logs* logs, void* stream) {
   if (!h || !g_dev || !stepsz_host || !phi_all || !rho_all || !alp_all) return fail(PDHG_ERR_ARG, "pdhg_multi_step: null argument");
   if (n_maxiter < 1) return fail(PDHG_ERR_ARG, "pdhg_multi_step: n_maxiter must be >= 1");
-  CU(cudaSetDevice(h->cfg.device));
+  DeviceGuard guard(h->cfg.device);
+  if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
   return multi_step_impl(h, g_dev, epsl_host, stepsz_host, n_maxiter, print_freq, phi_all, rho_all, alp_all, logs,
                          static_cast<cudaStream_t>(stream));
 }
@@ -498,7 +571,8 @@ extern "C" int pdhg_multi_step_host(pdhg_handle* h, const double* g_host, const 
   if (!h || !g_host || !stepsz_host || !phi_all_host || !rho_all_host || !alp_all_host)
     return fail(PDHG_ERR_ARG, "pdhg_multi_step_host: null argument");
   if (n_maxiter < 1) return fail(PDHG_ERR_ARG, "pdhg_multi_step_host: n_maxiter must be >= 1");
-  CU(cudaSetDevice(h->cfg.device));
+  DeviceGuard guard(h->cfg.device);
+  if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
   const pdhg_config& c = h->cfg;
   const size_t B = h->B, n = h->n, nt = (size_t)c.nblocks * c.K + 1;
   const size_t n_phi = B * nt * n, n_rho = B * (nt - 1) * n, n_alp = B * h->A * (nt - 1) * n * c.n_ctrl;
@@ -524,7 +598,8 @@ extern "C" int pdhg_update_primal(pdhg_handle* h, const double* phi_prev, const 
                                   const double* epsl_host, double tau, double* phi_next, void* stream) {
   if (!h || !phi_prev || !rho_prev || !alp_prev || !phi_next) return fail(PDHG_ERR_ARG, "pdhg_update_primal: null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  CU(cudaSetDevice(h->cfg.device));
+  DeviceGuard guard(h->cfg.device);
+  if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
   const pdhg_config& c = h->cfg;
   const size_t B = h->B, kn = (size_t)c.K * h->n;
   int rc = upload_scalars(h, epsl_host, nullptr, s);
@@ -543,7 +618,8 @@ extern "C" int pdhg_update_dual(pdhg_handle* h, const double* phi_bar, const dou
                                 int32_t* n_inner_host, double* err_host, void* stream) {
   if (!h || !phi_bar || !rho_prev || !alp_prev || !rho_next || !alp_next) return fail(PDHG_ERR_ARG, "pdhg_update_dual: null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  CU(cudaSetDevice(h->cfg.device));
+  DeviceGuard guard(h->cfg.device);
+  if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
   const pdhg_config& c = h->cfg;
   const size_t B = h->B, kn = (size_t)c.K * h->n;
   int rc = upload_scalars(h, epsl_host, nullptr, s);

@@ -64,7 +64,9 @@ struct CoopArgs {
   int ky_off, nyh_tab;       // phase B on an exchanged ky-slab: offset and row length of the per-mode table; default 0, nyh
   double* ext_sums;          // MODE_PHASE: device array [kNV = 20] receiving the grid totals of phases D / E (may be null)
   int dbg_phase, dbg_pass;   // MODE_PHASE (profiling): phase id 0..3 = A,B,C,D and pass mask of phase B (bit 0,1,2)
-  int d_pipe;         // 1: cp.async-pipelined dual sweep (ny even and the staging buffers fit shared memory)
+  int tma_d;          // 1: dual sweep through the TMA row pipeline (phase_D_tma); tma_R rows per tile, tma_S ring stages at most
+  int tma_R, tma_S;
+  int work_bytes;     // size of the work area (FFT buffers / accumulator slots / TMA ring)
   int fast_y, fast_x; // warp-private 256-point transforms along y (phases A, C) / along x (phase B)
   int d_fuse;         // max. inner dual sweeps fused per pass while the inner loop is long (1 = off; PDHG_DFUSE=n overrides)
   double dxe, dye;
@@ -87,16 +89,25 @@ struct CoopArgs {
 extern __shared__ __align__(16) unsigned char g_sm[];
 constexpr int kArgsBytes = (int)((sizeof(CoopArgs) + 15) / 16 * 16);
 constexpr int kRedBytes = kNQ * kWarps * 8;
+constexpr int kBarBytes = 128;    // mbarriers of the TMA row pipelines: full[8], empty[8]
 __device__ __forceinline__ const CoopArgs& cargs() { return *reinterpret_cast<const CoopArgs*>(g_sm); }
+
+// TMA row pipelines (phase_D_tma ...): ring state kept by every thread; the mbarriers full[8], empty[8] live in shared memory
+// behind the reduction scratch and are initialised once per launch (full: 1 arrival + transaction bytes, empty: one arrival
+// per consumer warp).  Bit s of par_full / par_empty = parity of the next phase to wait for on full[s] / empty[s].
+struct RowPipe { uint32_t par_full, par_empty; };
+constexpr int kPipeMaxStages = 8;
 
 struct Ctx {
   cg::grid_group grid;
+  RowPipe pipe;
   int o_twy, o_cx, o_cy, o_work;     // byte offsets of the tables and of the FFT / staging buffers
   int epoch;
   float inv_nx, inv_nchunk;          // float reciprocals for division-free index math
   unsigned long long tsub[10], tl;   // diagnostic sub-phase timers (CTA 0, thread 0 only)
   __device__ __forceinline__ double* red() const { return reinterpret_cast<double*>(g_sm + kArgsBytes); }
-  __device__ __forceinline__ const double2* twx() const { return reinterpret_cast<const double2*>(g_sm + kArgsBytes + kRedBytes); }
+  __device__ __forceinline__ uint64_t* bars() const { return reinterpret_cast<uint64_t*>(g_sm + kArgsBytes + kRedBytes); }
+  __device__ __forceinline__ const double2* twx() const { return reinterpret_cast<const double2*>(g_sm + kArgsBytes + kRedBytes + kBarBytes); }
   __device__ __forceinline__ const double2* twy() const { return reinterpret_cast<const double2*>(g_sm + o_twy); }
   __device__ __forceinline__ const double* cx() const { return reinterpret_cast<const double*>(g_sm + o_cx); }
   __device__ __forceinline__ const double* cy() const { return reinterpret_cast<const double*>(g_sm + o_cy); }
@@ -117,7 +128,7 @@ struct Ctx {
       const int vw = (a.nye & 1) ? 1 : 2;
       inv_nchunk = 1.0f / (float)(((a.nye / vw) + 31) >> 5);
     }
-    const int o_twx = kArgsBytes + kRedBytes;
+    const int o_twx = kArgsBytes + kRedBytes + kBarBytes;
     o_twy = o_twx + 16 * a.nxe;
     o_cx = o_twy + 16 * a.nye;
     o_cy = o_cx + 8 * a.nxe;
@@ -128,6 +139,11 @@ struct Ctx {
     double* py = reinterpret_cast<double*>(g_sm + o_cy);
     for (int i = threadIdx.x; i < a.nxe; i += blockDim.x) { tx[i] = a.tw_xe[i]; px[i] = a.coef_xe[i]; }
     for (int i = threadIdx.x; i < a.nye; i += blockDim.x) { ty[i] = a.tw_ye[i]; py[i] = a.coef_ye[i]; }
+    pipe.par_full = 0u; pipe.par_empty = 0u;
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < kPipeMaxStages; ++s) { mbar_init(bars() + s, 1); mbar_init(bars() + kPipeMaxStages + s, kWarps); }
+      mbar_fence_init();
+    }
     __syncthreads();
   }
 };
@@ -975,40 +991,154 @@ __device__ __forceinline__ void dual_point(int egno, double c0, double cxm, doub
   rn = relu_nan(ro + sigma * vec);
 }
 
-// ---- phase D: one dual sweep.  src -> dst (may alias); outer differences against `ref` when HASREF.
-// CTA partials: slots 0..1 rho (diff^2, next^2), 2+2q..3+2q alp q; 10 outer rho diff^2, 11+q outer alp diff^2; 15 NaN count of rho_next
+// ---- phase D: dual sweep(s).  src -> dst (may alias when NS == 1 and the direct-load variant runs).
+// CTA partials: slots 0..1 rho (diff^2, next^2), 2+2q..3+2q alp q; 15 NaN count of rho_next  (10..14 belong to phase E)
 // NS = 2 fuses two consecutive sweeps into one pass over memory: the dual update at a point needs phi_bar's stencil but only the
 // point's own rho / alp, so the second sweep runs on the first one's results while they are still in registers (same arithmetic
 // per point, same per-thread summation order => bit-identical iterates and error sums; its sums go to slots 20..35).
 // With NS = 2, `nx_sw` (0..kFuseMax-2) further sweeps follow in the same pass; their sums are accumulated in per-thread
-// shared-memory slots (the transform buffers are idle during this phase; same order of additions as registers would see) and
-// go to slots 36.. .
-template <int ND, int VW, bool HASREF, int EG, int NS = 1, bool XTRA = false>
+// shared-memory slots (same order of additions as registers would see) and go to slots 36.. .
+template <int NA> struct DualSums {     // per-thread running sums of one pass: sweep 1 (s_*) and sweep 2 of a fused pair (t_*)
+  double s_dr, s_rr, s_nan, s_da[NA], s_aa[NA];
+  double t_dr, t_rr, t_nan, t_da[NA], t_aa[NA];
+  __device__ __forceinline__ void clear() {
+    s_dr = s_rr = s_nan = t_dr = t_rr = t_nan = 0.0;
+#pragma unroll
+    for (int q = 0; q < NA; ++q) { s_da[q] = s_aa[q] = t_da[q] = t_aa[q] = 0.0; }
+  }
+};
+template <int NA> struct DualAccLayout { static constexpr int kAcc = 3 + 2 * NA; };   // shared-memory slots per extra sweep and thread
+
+// all sweeps of one pass for the VW-wide item at column j, operands in registers: cc = phi_bar[k+1] at the item, pk = phi_bar[k],
+// (cxm, cxp) = phi_bar[k+1] at the x-neighbours, (c_l, c_r) = its y-neighbours left of / right of the item, (ro, ao) = the prox centre
+template <int ND, int VW, int EG, int NS, bool XTRA>
+__device__ __forceinline__ void dual_item(const Ctx& c, const Vec<VW>& cc, const Vec<VW>& pk, const Vec<VW>& ro, const Vec<VW> (&ao)[2 * ND],
+                                          const Vec<VW>& cxm, const Vec<VW>& cxp, double c_l, double c_r, double cx, int j, double wxm,
+                                          double wxp, bool acc_on, double sigma, double epsl, const Recip& rc, int nx_sw, double* xacc,
+                                          int astr, DualSums<2 * ND>& S, Vec<VW>& rn, Vec<VW> (&an)[2 * ND]) {
+  constexpr int NA = 2 * ND, egno = EG;
+  constexpr int kAcc = DualAccLayout<NA>::kAcc;
+#pragma unroll
+  for (int e = 0; e < VW; ++e) {
+    const double cym = (e == 0) ? c_l : cc.e[0], cyp = (e == VW - 1) ? c_r : cc.e[VW - 1];
+    double aoe[NA], ane[NA], rne;
+#pragma unroll
+    for (int q = 0; q < NA; ++q) aoe[q] = ao[q].e[e];
+    dual_point<ND>(egno, cc.e[e], (ND == 2) ? cxm.e[e] : 0.0, (ND == 2) ? cxp.e[e] : 0.0, cym, cyp, pk.e[e], ro.e[e], aoe, cx,
+                   c.cy()[j + e], wxm, wxp, sigma, epsl, rc, rne, ane);
+    if (acc_on) {
+      double d = rne - ro.e[e];
+      S.s_dr += d * d; S.s_rr += rne * rne; S.s_nan += is_nan(rne) ? 1.0 : 0.0;
+#pragma unroll
+      for (int q = 0; q < NA; ++q) { d = ane[q] - aoe[q]; S.s_da[q] += d * d; S.s_aa[q] += ane[q] * ane[q]; }
+    }
+    if (NS == 2) {
+      double an2[NA], rn2;
+      dual_point<ND>(egno, cc.e[e], (ND == 2) ? cxm.e[e] : 0.0, (ND == 2) ? cxp.e[e] : 0.0, cym, cyp, pk.e[e], rne, ane, cx,
+                     c.cy()[j + e], wxm, wxp, sigma, epsl, rc, rn2, an2);
+      if (acc_on) {
+        double d = rn2 - rne;
+        S.t_dr += d * d; S.t_rr += rn2 * rn2; S.t_nan += is_nan(rn2) ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < NA; ++q) { d = an2[q] - ane[q]; S.t_da[q] += d * d; S.t_aa[q] += an2[q] * an2[q]; }
+      }
+      rne = rn2;
+#pragma unroll
+      for (int q = 0; q < NA; ++q) ane[q] = an2[q];
+    }
+    rn.e[e] = rne;
+#pragma unroll
+    for (int q = 0; q < NA; ++q) an[q].e[e] = ane[q];
+  }
+  if (XTRA) {
+    // further sweeps of the fused pass: the VW points of the item advance together (independent chains for the fp64
+    // pipe), each sum is read from / written to its shared-memory slot once per item, additions in the order e = 0, 1
+#pragma unroll 1
+    for (int sw = 0; sw < nx_sw; ++sw) {
+      double rn2[VW], an2[VW][NA];
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        const double cym = (e == 0) ? c_l : cc.e[0], cyp = (e == VW - 1) ? c_r : cc.e[VW - 1];
+        double aoe[NA];
+#pragma unroll
+        for (int q = 0; q < NA; ++q) aoe[q] = an[q].e[e];
+        dual_point<ND>(egno, cc.e[e], (ND == 2) ? cxm.e[e] : 0.0, (ND == 2) ? cxp.e[e] : 0.0, cym, cyp, pk.e[e], rn.e[e], aoe, cx,
+                       c.cy()[j + e], wxm, wxp, sigma, epsl, rc, rn2[e], an2[e]);
+      }
+      if (acc_on) {
+        double* as = xacc + sw * kAcc * astr;
+        double s0 = as[0], s1 = as[astr], s2 = as[2 * astr];
+#pragma unroll
+        for (int e = 0; e < VW; ++e) { const double d = rn2[e] - rn.e[e]; s0 += d * d; s1 += rn2[e] * rn2[e]; s2 += is_nan(rn2[e]) ? 1.0 : 0.0; }
+        as[0] = s0; as[astr] = s1; as[2 * astr] = s2;
+#pragma unroll
+        for (int q = 0; q < NA; ++q) {
+          double sd = as[(3 + 2 * q) * astr], sa = as[(4 + 2 * q) * astr];
+#pragma unroll
+          for (int e = 0; e < VW; ++e) { const double d = an2[e][q] - an[q].e[e]; sd += d * d; sa += an2[e][q] * an2[e][q]; }
+          as[(3 + 2 * q) * astr] = sd; as[(4 + 2 * q) * astr] = sa;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        rn.e[e] = rn2[e];
+#pragma unroll
+        for (int q = 0; q < NA; ++q) an[q].e[e] = an2[e][q];
+      }
+    }
+  }
+}
+
+// block-reduce the per-thread sums of a pass into the CTA partial rows (slots 0..15, 20..35, 36 + 16 sw ..)
+template <int ND, int NS, bool XTRA>
+__device__ __forceinline__ void dual_publish(Ctx& c, const DualSums<2 * ND>& S, int nx_sw, const double* xacc, int astr) {
+  constexpr int NA = 2 * ND, kAcc = DualAccLayout<NA>::kAcc;
+  double sums[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) sums[q] = 0.0;
+  sums[0] = S.s_dr; sums[1] = S.s_rr; sums[15] = S.s_nan;
+#pragma unroll
+  for (int q = 0; q < NA; ++q) { sums[2 + 2 * q] = S.s_da[q]; sums[3 + 2 * q] = S.s_aa[q]; }
+  cta_partials<16>(c, sums, 0);
+  if (NS == 2) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) sums[q] = 0.0;
+    sums[0] = S.t_dr; sums[1] = S.t_rr; sums[15] = S.t_nan;
+#pragma unroll
+    for (int q = 0; q < NA; ++q) { sums[2 + 2 * q] = S.t_da[q]; sums[3 + 2 * q] = S.t_aa[q]; }
+    cta_partials<16>(c, sums, 20);
+    for (int sw = 0; sw < (XTRA ? nx_sw : 0); ++sw) {
+      const double* as = xacc + sw * kAcc * astr;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) sums[q] = 0.0;
+      sums[0] = as[0]; sums[1] = as[astr]; sums[15] = as[2 * astr];
+#pragma unroll
+      for (int q = 0; q < NA; ++q) { sums[2 + 2 * q] = as[(3 + 2 * q) * astr]; sums[3 + 2 * q] = as[(4 + 2 * q) * astr]; }
+      cta_partials<16>(c, sums, 36 + 16 * sw);
+    }
+  }
+}
+
+// direct-load variant: thread-linear grid-stride over VW-wide items, operands global -> registers (any grid, 1-D and 2-D)
+template <int ND, int VW, int EG, int NS = 1, bool XTRA = false>
 __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d, double* alp_d,
-                        const double* rho_ref, const double* alp_ref, double sigma, double epsl, int nx_sw = 0) {
+                                     double sigma, double epsl, int nx_sw = 0) {
   phib = as_global(phib); rho_s = as_global(rho_s); alp_s = as_global(alp_s); rho_d = as_global(rho_d); alp_d = as_global(alp_d);
-  if (HASREF) { rho_ref = as_global(rho_ref); alp_ref = as_global(alp_ref); }
   constexpr int NA = 2 * ND;
   const CoopArgs& a = cargs();
   const MarchParams& p = a.p;
   const int K = p.K, nx = a.nxe, ny = a.nye;
-  constexpr int egno = EG;                 // compile-time problem id: the other prox variants are not even compiled in
   const size_t n = (size_t)nx * ny, KN = (size_t)K * n;
   const Recip rc(p.dt, a.dxe, a.dye, sigma);
   const int ny2 = ny / VW;
-  double s_dr = 0.0, s_rr = 0.0, s_or = 0.0, s_nan = 0.0;
-  double s_da[NA], s_aa[NA], s_oa[NA];
-  double t_dr = 0.0, t_rr = 0.0, t_nan = 0.0, t_da[NA], t_aa[NA];      // second sweep of a fused pair (NS == 2)
-#pragma unroll
-  for (int q = 0; q < NA; ++q) { s_da[q] = 0.0; s_aa[q] = 0.0; s_oa[q] = 0.0; t_da[q] = 0.0; t_aa[q] = 0.0; }
-  // sums of the extra sweeps: xacc[(sw * kAcc + q) * blockDim], q = 0 rho diff^2, 1 rho next^2, 2 NaN count, 3 + 2 t / 4 + 2 t alp t
-  constexpr int kAcc = 3 + 2 * NA;
+  DualSums<NA> S;
+  S.clear();
+  constexpr int kAcc = DualAccLayout<NA>::kAcc;
   double* xacc = reinterpret_cast<double*>(c.work()) + threadIdx.x;
   const int astr = blockDim.x;
   if (XTRA) {
     for (int q = 0; q < nx_sw * kAcc; ++q) xacc[q * astr] = 0.0;
   }
-  // thread-linear grid-stride over VW-wide items: consecutive threads of a CTA take consecutive items of a row
   const float inv_ny2 = 1.0f / (float)ny2;
   const long long items = (long long)K * nx * ny2, istride = (long long)gridDim.x * blockDim.x;
   for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += istride) {
@@ -1028,267 +1158,142 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
     const Nbr bx = nbr(i, nx, p.bc_x);
     if (ND == 2) { cxm = ldv<VW>(pb1 + (size_t)bx.m * ny + j); cxp = ldv<VW>(pb1 + (size_t)bx.p * ny + j); }
     const double c_l = ldg1(pb1 + row + jm), c_r = ldg1(pb1 + row + jq);
-    Vec<VW> rref, aref[NA];
-    if (HASREF) {
-      rref = ldv<VW>(rho_ref + g);
-#pragma unroll
-      for (int q = 0; q < NA; ++q) aref[q] = ldv<VW>(alp_ref + (size_t)q * KN + g);
-    }
-    const double cx = (ND == 2 || egno == 3) ? c.cx()[i] : 0.0;
+    const double cx = (ND == 2 || EG == 3) ? c.cx()[i] : 0.0;
     const bool acc_on = (i >= a.sum_lo && i < a.sum_hi);
     Vec<VW> rn, an[NA];
-#pragma unroll
-    for (int e = 0; e < VW; ++e) {
-      const double cym = (e == 0) ? c_l : cc.e[0], cyp = (e == VW - 1) ? c_r : cc.e[VW - 1];
-      double aoe[NA], ane[NA], rne;
-#pragma unroll
-      for (int q = 0; q < NA; ++q) aoe[q] = ao[q].e[e];
-      dual_point<ND>(egno, cc.e[e], (ND == 2) ? cxm.e[e] : 0.0, (ND == 2) ? cxp.e[e] : 0.0, cym, cyp, pk.e[e], ro.e[e], aoe, cx,
-                     c.cy()[j + e], bx.wm, bx.wp, sigma, epsl, rc, rne, ane);
-      if (acc_on) {
-        double d = rne - ro.e[e];
-        s_dr += d * d; s_rr += rne * rne; s_nan += is_nan(rne) ? 1.0 : 0.0;
-        if (HASREF) { d = rne - rref.e[e]; s_or += d * d; }
-#pragma unroll
-        for (int q = 0; q < NA; ++q) {
-          d = ane[q] - aoe[q];
-          s_da[q] += d * d; s_aa[q] += ane[q] * ane[q];
-          if (HASREF) { d = ane[q] - aref[q].e[e]; s_oa[q] += d * d; }
-        }
-      }
-      if (NS == 2) {
-        double an2[NA], rn2;
-        dual_point<ND>(egno, cc.e[e], (ND == 2) ? cxm.e[e] : 0.0, (ND == 2) ? cxp.e[e] : 0.0, cym, cyp, pk.e[e], rne, ane, cx,
-                       c.cy()[j + e], bx.wm, bx.wp, sigma, epsl, rc, rn2, an2);
-        if (acc_on) {
-          double d = rn2 - rne;
-          t_dr += d * d; t_rr += rn2 * rn2; t_nan += is_nan(rn2) ? 1.0 : 0.0;
-#pragma unroll
-          for (int q = 0; q < NA; ++q) { d = an2[q] - ane[q]; t_da[q] += d * d; t_aa[q] += an2[q] * an2[q]; }
-        }
-        rne = rn2;
-#pragma unroll
-        for (int q = 0; q < NA; ++q) ane[q] = an2[q];
-      }
-      rn.e[e] = rne;
-#pragma unroll
-      for (int q = 0; q < NA; ++q) an[q].e[e] = ane[q];
-    }
-    if (XTRA) {
-      // further sweeps of the fused pass: the VW points of the item advance together (independent chains for the fp64
-      // pipe), each sum is read from / written to its shared-memory slot once per item, additions in the order e = 0, 1
-#pragma unroll 1
-      for (int sw = 0; sw < nx_sw; ++sw) {
-        double rn2[VW], an2[VW][NA];
-#pragma unroll
-        for (int e = 0; e < VW; ++e) {
-          const double cym = (e == 0) ? c_l : cc.e[0], cyp = (e == VW - 1) ? c_r : cc.e[VW - 1];
-          double aoe[NA];
-#pragma unroll
-          for (int q = 0; q < NA; ++q) aoe[q] = an[q].e[e];
-          dual_point<ND>(egno, cc.e[e], (ND == 2) ? cxm.e[e] : 0.0, (ND == 2) ? cxp.e[e] : 0.0, cym, cyp, pk.e[e], rn.e[e], aoe, cx,
-                         c.cy()[j + e], bx.wm, bx.wp, sigma, epsl, rc, rn2[e], an2[e]);
-        }
-        if (acc_on) {
-          double* as = xacc + sw * kAcc * astr;
-          double s0 = as[0], s1 = as[astr], s2 = as[2 * astr];
-#pragma unroll
-          for (int e = 0; e < VW; ++e) { const double d = rn2[e] - rn.e[e]; s0 += d * d; s1 += rn2[e] * rn2[e]; s2 += is_nan(rn2[e]) ? 1.0 : 0.0; }
-          as[0] = s0; as[astr] = s1; as[2 * astr] = s2;
-#pragma unroll
-          for (int q = 0; q < NA; ++q) {
-            double sd = as[(3 + 2 * q) * astr], sa = as[(4 + 2 * q) * astr];
-#pragma unroll
-            for (int e = 0; e < VW; ++e) { const double d = an2[e][q] - an[q].e[e]; sd += d * d; sa += an2[e][q] * an2[e][q]; }
-            as[(3 + 2 * q) * astr] = sd; as[(4 + 2 * q) * astr] = sa;
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < VW; ++e) {
-          rn.e[e] = rn2[e];
-#pragma unroll
-          for (int q = 0; q < NA; ++q) an[q].e[e] = an2[e][q];
-        }
-      }
-    }
+    dual_item<ND, VW, EG, NS, XTRA>(c, cc, pk, ro, ao, cxm, cxp, c_l, c_r, cx, j, bx.wm, bx.wp, acc_on, sigma, epsl, rc, nx_sw, xacc, astr, S,
+                                    rn, an);
     stv<VW>(rho_d + g, rn);
 #pragma unroll
     for (int q = 0; q < NA; ++q) stv<VW>(alp_d + (size_t)q * KN + g, an[q]);
   }
   c.tick(5);
-  double sums[16];
-#pragma unroll
-  for (int q = 0; q < 16; ++q) sums[q] = 0.0;
-  sums[0] = s_dr; sums[1] = s_rr; sums[10] = s_or; sums[15] = s_nan;
-#pragma unroll
-  for (int q = 0; q < NA; ++q) { sums[2 + 2 * q] = s_da[q]; sums[3 + 2 * q] = s_aa[q]; sums[11 + q] = s_oa[q]; }
-  cta_partials<16>(c, sums, 0);
-  if (NS == 2) {
-#pragma unroll
-    for (int q = 0; q < 16; ++q) sums[q] = 0.0;
-    sums[0] = t_dr; sums[1] = t_rr; sums[15] = t_nan;
-#pragma unroll
-    for (int q = 0; q < NA; ++q) { sums[2 + 2 * q] = t_da[q]; sums[3 + 2 * q] = t_aa[q]; }
-    cta_partials<16>(c, sums, 20);
-    for (int sw = 0; sw < (XTRA ? nx_sw : 0); ++sw) {
-      const double* as = xacc + sw * kAcc * astr;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) sums[q] = 0.0;
-      sums[0] = as[0]; sums[1] = as[astr]; sums[15] = as[2 * astr];
-#pragma unroll
-      for (int q = 0; q < NA; ++q) { sums[2 + 2 * q] = as[(3 + 2 * q) * astr]; sums[3 + 2 * q] = as[(4 + 2 * q) * astr]; }
-      cta_partials<16>(c, sums, 36 + 16 * sw);
-    }
-  }
+  dual_publish<ND, NS, XTRA>(c, S, nx_sw, xacc, astr);
 }
 
-// ---- phase D, software-pipelined: every warp stages the inputs of its NEXT (row, 64-point chunk) unit in shared memory
-// with cp.async while it computes the current one, so global-load latency overlaps the fp64 work without holding
-// registers (the plain version above serialises load -> compute -> store per warp).  Needs ny even (16-byte copies).
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async16_ca(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// ---- TMA row pipeline (2-D grids with an even number of columns) -----------------------------------------------------
+// A tile = the R x-rows [i0, i0 + R) of one time row k.  ONE thread of the CTA streams the tile's operand rows — phi_bar[k+1]
+// rows i0-1 .. i0+R (the x-halo comes with it), phi_bar[k], rho and the 4 control arrays: (7 R + 2) rows of ny doubles — into
+// an S-stage shared-memory ring with bulk asynchronous copies (cp.async.bulk, one instruction per array), S - 1 tiles ahead
+// of the consumers.  All 16 warps consume: wait on the stage's `full` mbarrier (transaction bytes), read their operands with
+// LDS.128 at immediate offsets (no global address arithmetic, no load registers held across the wait, every phi_bar row is
+// fetched from L2 once per tile instead of three times), compute, store the results straight from registers (coalesced
+// 16-byte STG), and release the stage on its `empty` mbarrier.  Bytes in flight per SM are set by the ring (>= 64 KB), not
+// by occupancy.  Per-point arithmetic is dual_item's, i.e. the same as the direct-load variant's, bit for bit.
 
-template <int ND> struct DStage {   // doubles per staged unit: cc[64] + 2 halos, then 64 each: pk, ro, ao[2 ND], (cxm, cxp)
-  static constexpr int kArr = 2 + 2 * ND + (ND == 2 ? 2 : 0);
-  static constexpr int kDoubles = 64 + 2 + 64 * kArr + 2;     // padded to a multiple of 4 doubles
-  static constexpr int kBytes = kDoubles * 8;
-};
-
-template <int ND, bool HASREF>
-__device__ __noinline__ void phase_D_pipe(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d,
-                                          double* alp_d, const double* rho_ref, const double* alp_ref, double sigma, double epsl) {
+template <int EG, int NS, bool XTRA>
+__device__ __noinline__ void phase_D_tma(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d,
+                                         double* alp_d, double sigma, double epsl, int nx_sw = 0) {
   phib = as_global(phib); rho_s = as_global(rho_s); alp_s = as_global(alp_s); rho_d = as_global(rho_d); alp_d = as_global(alp_d);
-  if (HASREF) { rho_ref = as_global(rho_ref); alp_ref = as_global(alp_ref); }
-  constexpr int NA = 2 * ND, VW = 2;
-  using ST = DStage<ND>;
+  constexpr int ND = 2, NA = 4, VW = 2;
   const CoopArgs& a = cargs();
   const MarchParams& p = a.p;
-  const int K = p.K, nx = a.nxe, ny = a.nye, egno = p.egno;
+  const int K = p.K, nx = a.nxe, ny = a.nye;
   const size_t n = (size_t)nx * ny, KN = (size_t)K * n;
   const Recip rc(p.dt, a.dxe, a.dye, sigma);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const int ny2 = ny / VW, nchunk = (ny2 + 31) >> 5;
-  const long long units = (long long)K * nx * nchunk, ustride = (long long)gridDim.x * nwarp;
-  double* stage0 = reinterpret_cast<double*>(c.work()) + (size_t)warp * 2 * ST::kDoubles;
-  double s_dr = 0.0, s_rr = 0.0, s_or = 0.0, s_nan = 0.0;
-  double s_da[NA], s_aa[NA], s_oa[NA];
-#pragma unroll
-  for (int q = 0; q < NA; ++q) { s_da[q] = 0.0; s_aa[q] = 0.0; s_oa[q] = 0.0; }
-
-  auto decode = [&](long long unit, int& k, int& i, int& ch) {
-    const int r = (units < (1LL << 24)) ? fast_div_exact((int)unit, nchunk, c.inv_nchunk) : (int)(unit / nchunk);
-    ch = (int)(unit - (long long)r * nchunk);
-    k = fast_div_exact(r, nx, c.inv_nx);
-    i = r - k * nx;
-  };
-  auto issue = [&](long long unit, double* st) {
-    int k, i, ch;
-    decode(unit, k, i, ch);
-    const int nvalid = min(32, ny2 - ch * 32);
-    const int j0 = ch * 64;
-    const size_t row = (size_t)i * ny, g0 = (size_t)k * n + row + j0;
-    const double* pb1 = phib + (size_t)(k + 1) * n;
-    if (lane < nvalid) {
-      const int o = 2 * lane;
-      cp_async16_ca(st + o, pb1 + row + j0 + o);
-      double* q = st + 66;
-      cp_async16(q + o, phib + g0 + o); q += 64;
-      cp_async16(q + o, rho_s + g0 + o); q += 64;
-#pragma unroll
-      for (int t = 0; t < NA; ++t) { cp_async16(q + o, alp_s + (size_t)t * KN + g0 + o); q += 64; }
-      if (ND == 2) {
-        const Nbr bx = nbr(i, nx, p.bc_x);
-        cp_async16_ca(q + o, pb1 + (size_t)bx.m * ny + j0 + o); q += 64;
-        cp_async16_ca(q + o, pb1 + (size_t)bx.p * ny + j0 + o);
-      }
-    }
-    if (lane == 0) cp_async8(st + 64, pb1 + row + ((j0 == 0) ? ny - 1 : j0 - 1));
-    if (lane == 1) { const int je = j0 + 2 * nvalid; cp_async8(st + 65, pb1 + row + ((je == ny) ? 0 : je)); }
-  };
-
-  long long unit = (long long)blockIdx.x * nwarp + warp;
-  int sidx = 0;
-  if (unit < units) issue(unit, stage0);
-  cp_async_commit();
-  for (; unit < units; unit += ustride) {
-    const long long un = unit + ustride;
-    double* st = stage0 + (size_t)sidx * ST::kDoubles;
-    if (un < units) issue(un, stage0 + (size_t)(sidx ^ 1) * ST::kDoubles);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncwarp();
-    int k, i, ch;
-    decode(unit, k, i, ch);
-    const int nvalid = min(32, ny2 - ch * 32);
-    if (lane < nvalid) {
-      const int j = ch * 64 + 2 * lane, o = 2 * lane;
-      const size_t g = (size_t)k * n + (size_t)i * ny + j;
-      const double2 cc = *reinterpret_cast<const double2*>(st + o);
-      const double c_l = (lane == 0) ? st[64] : st[o - 1];
-      const double c_r = (lane == nvalid - 1) ? st[65] : st[o + 2];
-      const double* q = st + 66;
-      const double2 pk = *reinterpret_cast<const double2*>(q + o); q += 64;
-      const double2 ro = *reinterpret_cast<const double2*>(q + o); q += 64;
-      double2 ao[NA];
-#pragma unroll
-      for (int t = 0; t < NA; ++t) { ao[t] = *reinterpret_cast<const double2*>(q + o); q += 64; }
-      double2 cxm = make_double2(0.0, 0.0), cxp = cxm;
-      const Nbr bx = nbr(i, nx, p.bc_x);
-      if (ND == 2) { cxm = *reinterpret_cast<const double2*>(q + o); q += 64; cxp = *reinterpret_cast<const double2*>(q + o); }
-      Vec<VW> rref, aref[NA];
-      if (HASREF) {
-        rref = ldv<VW>(rho_ref + g);
-#pragma unroll
-        for (int t = 0; t < NA; ++t) aref[t] = ldv<VW>(alp_ref + (size_t)t * KN + g);
-      }
-      const double cx = (ND == 2 || egno == 3) ? c.cx()[i] : 0.0;
-      Vec<VW> rn, an[NA];
-#pragma unroll
-      for (int e = 0; e < VW; ++e) {
-        const double c0 = e ? cc.y : cc.x;
-        const double cym = e ? cc.x : c_l, cyp = e ? c_r : cc.y;
-        double aoe[NA], ane[NA], rne;
-#pragma unroll
-        for (int t = 0; t < NA; ++t) aoe[t] = e ? ao[t].y : ao[t].x;
-        const double roe = e ? ro.y : ro.x;
-        dual_point<ND>(egno, c0, e ? cxm.y : cxm.x, e ? cxp.y : cxp.x, cym, cyp, e ? pk.y : pk.x, roe, aoe, cx, c.cy()[j + e], bx.wm,
-                       bx.wp, sigma, epsl, rc, rne, ane);
-        rn.e[e] = rne;
-        double d = rne - roe;
-        s_dr += d * d; s_rr += rne * rne; s_nan += is_nan(rne) ? 1.0 : 0.0;
-        if (HASREF) { d = rne - rref.e[e]; s_or += d * d; }
-#pragma unroll
-        for (int t = 0; t < NA; ++t) {
-          an[t].e[e] = ane[t];
-          d = ane[t] - aoe[t];
-          s_da[t] += d * d; s_aa[t] += ane[t] * ane[t];
-          if (HASREF) { d = ane[t] - aref[t].e[e]; s_oa[t] += d * d; }
-        }
-      }
-      stv<VW>(rho_d + g, rn);
-#pragma unroll
-      for (int t = 0; t < NA; ++t) stv<VW>(alp_d + (size_t)t * KN + g, an[t]);
-    }
-    __syncwarp();     // every lane is done with this stage before it is refilled in the next round
-    sidx ^= 1;
+  const int ny2 = ny >> 1;
+  const int R = a.tma_R;
+  constexpr int kAcc = DualAccLayout<NA>::kAcc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int astr = blockDim.x;
+  double* xacc = reinterpret_cast<double*>(c.work()) + tid;
+  if (XTRA) {
+    for (int q = 0; q < nx_sw * kAcc; ++q) xacc[q * astr] = 0.0;
   }
-  cp_async_wait<0>();
-  double sums[16];
+  // ring geometry: stages start after the accumulator slots of the extra sweeps
+  const int xbytes = XTRA ? ((nx_sw * kAcc * astr * 8 + 127) & ~127) : 0;
+  const int stage_d = (7 * R + 2) * ny;                                   // doubles per stage
+  int S = (a.work_bytes - xbytes) / (stage_d * 8);
+  if (S > a.tma_S) S = a.tma_S;
+  double* ring = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(c.work()) + xbytes);
+  uint64_t* full = c.bars();
+  uint64_t* empty = full + kPipeMaxStages;
+  const int ntx = (nx + R - 1) / R;                                       // tiles per time row
+  const int T = K * ntx, G = gridDim.x;
+  const float inv_ntx = 1.0f / (float)ntx, inv_ny2 = 1.0f / (float)ny2;
+  DualSums<NA> Sm;
+  Sm.clear();
+  // the ring overlays buffers the previous phase wrote through the generic proxy: order those accesses before the async-proxy
+  // writes of the bulk copies
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  // producer (warp 0): lane q issues copy q of the tile; lane 0 arms the barrier with the tile's byte count
+  auto produce = [&](int tile, int s) {
+    const int k = fast_div_exact(tile, ntx, inv_ntx), i0 = (tile - k * ntx) * R, nr = min(R, nx - i0);
+    mbar_wait(&empty[s], ((c.pipe.par_empty >> s) & 1u) ^ 1u);            // every consumer warp has released the stage
+    c.pipe.par_empty ^= (1u << s);
+    double* st = ring + (size_t)s * stage_d;
+    const uint32_t rowb = (uint32_t)ny * 8u;
+    if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)((nr + 2) + nr * (2 + NA)) * rowb);
+    __syncwarp();
+    const double* pb1 = phib + (size_t)(k + 1) * n;
+    const Nbr lo = nbr(i0, nx, p.bc_x), hi = nbr(i0 + nr - 1, nx, p.bc_x);
+    const size_t g0 = (size_t)k * n + (size_t)i0 * ny;
+    if (lane == 0) bulk_g2s(st, pb1 + (size_t)lo.m * ny, rowb, &full[s]);
+    else if (lane == 1) bulk_g2s(st + ny, pb1 + (size_t)i0 * ny, rowb * nr, &full[s]);
+    else if (lane == 2) bulk_g2s(st + (size_t)(nr + 1) * ny, pb1 + (size_t)hi.p * ny, rowb, &full[s]);
+    else if (lane == 3) bulk_g2s(st + (size_t)(R + 2) * ny, phib + g0, rowb * nr, &full[s]);
+    else if (lane == 4) bulk_g2s(st + (size_t)(2 * R + 2) * ny, rho_s + g0, rowb * nr, &full[s]);
+    else if (lane < 5 + NA) bulk_g2s(st + (size_t)(3 * R + 2 + (lane - 5) * R) * ny, alp_s + (size_t)(lane - 5) * KN + g0, rowb * nr, &full[s]);
+  };
+
+  int ps = 0;                                                             // producer stage cursor
+  if (warp == 0) {
+    for (int m = 0; m < S - 1; ++m) {
+      const int tm = blockIdx.x + m * G;
+      if (tm < T) produce(tm, ps);
+      if (++ps == S) ps = 0;
+    }
+  }
+  int cs = 0;                                                             // consumer stage cursor
+  for (int tile = blockIdx.x; tile < T; tile += G) {
+    if (warp == 0) {
+      const int tm = tile + (S - 1) * G;
+      if (tm < T) produce(tm, ps);
+      if (++ps == S) ps = 0;
+    }
+    const int k = fast_div_exact(tile, ntx, inv_ntx), i0 = (tile - k * ntx) * R, nr = min(R, nx - i0);
+    mbar_wait(&full[cs], (c.pipe.par_full >> cs) & 1u);
+    c.pipe.par_full ^= (1u << cs);
+    const double* st = ring + (size_t)cs * stage_d;
+    const int nitems = nr * ny2;
+    for (int it = tid; it < nitems; it += astr) {
+      const int r = fast_div_exact(it, ny2, inv_ny2), jp = it - r * ny2, j = 2 * jp, i = i0 + r;
+      const double* prow = st + (size_t)(r + 1) * ny;                     // phi_bar[k+1], row i
+      const int jm = (j == 0) ? ny - 1 : j - 1, jq = (j + 2 == ny) ? 0 : j + 2;
+      const double2 vcc = *reinterpret_cast<const double2*>(prow + j);
+      const double2 vxm = *reinterpret_cast<const double2*>(prow - ny + j);
+      const double2 vxp = *reinterpret_cast<const double2*>(prow + ny + j);
+      const double c_l = prow[jm], c_r = prow[jq];
+      const double* own = st + (size_t)(R + 2 + r) * ny + j;              // phi_bar[k], then rho, alp q at strides of R rows
+      const double2 vpk = *reinterpret_cast<const double2*>(own);
+      const double2 vro = *reinterpret_cast<const double2*>(own + (size_t)R * ny);
+      Vec<2> cc, pk, ro, cxm, cxp, ao[NA];
+      cc.e[0] = vcc.x; cc.e[1] = vcc.y; pk.e[0] = vpk.x; pk.e[1] = vpk.y; ro.e[0] = vro.x; ro.e[1] = vro.y;
+      cxm.e[0] = vxm.x; cxm.e[1] = vxm.y; cxp.e[0] = vxp.x; cxp.e[1] = vxp.y;
 #pragma unroll
-  for (int q = 0; q < 16; ++q) sums[q] = 0.0;
-  sums[0] = s_dr; sums[1] = s_rr; sums[10] = s_or; sums[15] = s_nan;
+      for (int q = 0; q < NA; ++q) {
+        const double2 v = *reinterpret_cast<const double2*>(own + (size_t)(2 + q) * R * ny);
+        ao[q].e[0] = v.x; ao[q].e[1] = v.y;
+      }
+      const Nbr bx = nbr(i, nx, p.bc_x);
+      const double cx = c.cx()[i];
+      const bool acc_on = (i >= a.sum_lo && i < a.sum_hi);
+      Vec<2> rn, an[NA];
+      dual_item<ND, VW, EG, NS, XTRA>(c, cc, pk, ro, ao, cxm, cxp, c_l, c_r, cx, j, bx.wm, bx.wp, acc_on, sigma, epsl, rc, nx_sw, xacc, astr, Sm,
+                                      rn, an);
+      const size_t g = (size_t)k * n + (size_t)i * ny + j;
+      stv<2>(rho_d + g, rn);
 #pragma unroll
-  for (int q = 0; q < NA; ++q) { sums[2 + 2 * q] = s_da[q]; sums[3 + 2 * q] = s_aa[q]; sums[11 + q] = s_oa[q]; }
-  cta_partials<16>(c, sums, 0);
+      for (int q = 0; q < NA; ++q) stv<2>(alp_d + (size_t)q * KN + g, an[q]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[cs]);                               // this warp is done reading the stage
+    if (++cs == S) cs = 0;
+  }
+  c.tick(5);
+  dual_publish<ND, NS, XTRA>(c, Sm, nx_sw, xacc, astr);
 }
 
 // ---- phase E (only after an inner loop of more than one sweep): outer-iteration differences of the dual variables,
@@ -1341,47 +1346,39 @@ __device__ __forceinline__ void run_C(Ctx& c, const double* pp, double* pn, doub
 }
 template <int EG>
 __device__ __forceinline__ void run_D_eg(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d, double* alp_d,
-                                         const double* rho_ref, const double* alp_ref, double sigma, double epsl, int ns) {
+                                         double sigma, double epsl, int ns) {
   const bool v2 = (cargs().nye & 1) == 0;
-  if (ns == 2) {        // fused sweeps (callers only ask for them without reference arrays)
-    if (cargs().has_x) { if (v2) phase_D<2, 2, false, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
-                         else phase_D<2, 1, false, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
-    else { if (v2) phase_D<1, 2, false, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
-           else phase_D<1, 1, false, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
+  if (cargs().tma_d) {      // 2-D, even ny (checked on the host): TMA row pipeline
+    if (ns == 1) phase_D_tma<EG, 1, false>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl);
+    else if (ns == 2) phase_D_tma<EG, 2, false>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl);
+    else phase_D_tma<EG, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl, ns - 2);
+    return;
+  }
+  if (ns == 2) {        // fused sweeps
+    if (cargs().has_x) { if (v2) phase_D<2, 2, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl);
+                         else phase_D<2, 1, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl); }
+    else { if (v2) phase_D<1, 2, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl);
+           else phase_D<1, 1, EG, 2>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl); }
     return;
   }
   if (ns > 2) {
-    if (cargs().has_x) { if (v2) phase_D<2, 2, false, EG, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl, ns - 2);
-                         else phase_D<2, 1, false, EG, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl, ns - 2); }
-    else { if (v2) phase_D<1, 2, false, EG, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl, ns - 2);
-           else phase_D<1, 1, false, EG, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl, ns - 2); }
+    if (cargs().has_x) { if (v2) phase_D<2, 2, EG, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl, ns - 2);
+                         else phase_D<2, 1, EG, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl, ns - 2); }
+    else { if (v2) phase_D<1, 2, EG, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl, ns - 2);
+           else phase_D<1, 1, EG, 2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl, ns - 2); }
     return;
   }
-  if (rho_ref) {
-    if (cargs().has_x) { if (v2) phase_D<2, 2, true, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
-                         else phase_D<2, 1, true, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl); }
-    else { if (v2) phase_D<1, 2, true, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
-           else phase_D<1, 1, true, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl); }
-  } else {
-    if (cargs().has_x) { if (v2) phase_D<2, 2, false, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
-                         else phase_D<2, 1, false, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
-    else { if (v2) phase_D<1, 2, false, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
-           else phase_D<1, 1, false, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
-  }
+  if (cargs().has_x) { if (v2) phase_D<2, 2, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl);
+                       else phase_D<2, 1, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl); }
+  else { if (v2) phase_D<1, 2, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl);
+         else phase_D<1, 1, EG>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl); }
 }
 __device__ __forceinline__ void run_D(Ctx& c, const double* phib, const double* rho_s, const double* alp_s, double* rho_d, double* alp_d,
-                                      const double* rho_ref, const double* alp_ref, double sigma, double epsl, int ns = 1) {
-  if (cargs().d_pipe && ns == 1) {
-    if (rho_ref) { if (cargs().has_x) phase_D_pipe<2, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl);
-                   else phase_D_pipe<1, true>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl); }
-    else { if (cargs().has_x) phase_D_pipe<2, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl);
-           else phase_D_pipe<1, false>(c, phib, rho_s, alp_s, rho_d, alp_d, nullptr, nullptr, sigma, epsl); }
-    return;
-  }
+                                      double sigma, double epsl, int ns = 1) {
   const int eg = cargs().p.egno;
-  if (eg == 1) run_D_eg<1>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl, ns);
-  else if (eg == 2) run_D_eg<2>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl, ns);
-  else run_D_eg<3>(c, phib, rho_s, alp_s, rho_d, alp_d, rho_ref, alp_ref, sigma, epsl, ns);
+  if (eg == 1) run_D_eg<1>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl, ns);
+  else if (eg == 2) run_D_eg<2>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl, ns);
+  else run_D_eg<3>(c, phib, rho_s, alp_s, rho_d, alp_d, sigma, epsl, ns);
 }
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -1453,7 +1450,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
       case 3: {
         // dbg_pass = number of sweeps to fuse in this pass (slab mode; 2 needs no shared memory, more only up to d_fuse)
         const int ns = (a.dbg_pass == 2 || (a.dbg_pass >= 3 && a.dbg_pass <= a.d_fuse)) ? a.dbg_pass : 1;
-        run_D(c, w.phib, w.rho[0], w.alp[0], w.rho[1], w.alp[1], nullptr, nullptr, a.op_step, epsl, ns);
+        run_D(c, w.phib, w.rho[0], w.alp[0], w.rho[1], w.alp[1], a.op_step, epsl, ns);
         grid_gather(c, v, 20 + 16 * (ns - 1));
         if (a.ext_sums && lead) {
           for (int q = kNV; q < 20 + 16 * (ns - 1); ++q) a.ext_sums[q] = gathered(c, q);
@@ -1497,7 +1494,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
     for (; j < p.rho_alp_iters; ++j) {
       double v[kNV];
       const int s = j & 1, d = s ^ 1;
-      run_D(c, a.op_phi_in, w.rho[s], w.alp[s], w.rho[d], w.alp[d], nullptr, nullptr, a.op_step, epsl);
+      run_D(c, a.op_phi_in, w.rho[s], w.alp[s], w.rho[d], w.alp[d], a.op_step, epsl);
       grid_gather(c, v);
       err = v[0] / v[1];
 #pragma unroll
@@ -1514,6 +1511,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
   // ------------------------------ MODE_MARCH ------------------------------
   double stepsz = p.stepsz[b];
   int status = ST_OK;
+  bool log_overflow = false;     // sticky: more periodic records than max_rec - 1 in some block (rows dropped, march goes on)
   int blocks_done = p.blk_begin;
   long long inner_total = 0;
   const int nt_all = p.nblocks * K + 1;
@@ -1578,7 +1576,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
           const int src = last, dst = (last == f1) ? f2 : f1;
           int ns = min(min(prev_j - j, p.rho_alp_iters - j), a.d_fuse);
           if (ns < 1) ns = 1;
-          run_D(c, w.phib, w.rho[src], w.alp[src], w.rho[dst], w.alp[dst], nullptr, nullptr, sigma, epsl, ns);
+          run_D(c, w.phib, w.rho[src], w.alp[src], w.rho[dst], w.alp[dst], sigma, epsl, ns);
           grid_gather(c, v, 20 + 16 * (ns - 1));
           c.tick(9);
           if (j == 0) { e1s0 = v[16]; e1s1 = v[17]; e1nan = v[18]; }
@@ -1600,7 +1598,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
           if (hit >= 0 && hit < ns - 1) {
             // exit inside the fused pass: redo exactly hit + 1 sweeps from the same (intact) input
             done_sw = hit + 1;
-            run_D(c, w.phib, w.rho[src], w.alp[src], w.rho[dst], w.alp[dst], nullptr, nullptr, sigma, epsl, done_sw);
+            run_D(c, w.phib, w.rho[src], w.alp[src], w.rho[dst], w.alp[dst], sigma, epsl, done_sw);
             grid_gather(c, v, 20 + 16 * (done_sw - 1));
           }
           // v[0..15] <- sums of the last sweep done
@@ -1684,7 +1682,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
         break;
       }
       if (lead) { p.iters[lb] = iters_done; p.stepsz_used[lb] = stepsz; p.nrec[lb] = nrec; p.end_reason[lb] = reason; }
-      if (logfull) status = ST_LOG_OVERFLOW;
+      log_overflow = log_overflow || logfull;
       if (reason == END_PAUSED) status = ST_PAUSED;
       const double* phi = w.phi[cp];
       const double* rho = w.rho[cd];
@@ -1714,7 +1712,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
   }
   TICK(5);
   if (lead) {
-    p.status[b] = status;
+    p.status[b] = (status == ST_OK && log_overflow) ? ST_LOG_OVERFLOW : status;   // overflow never stops the march (only NaN failure and pause do)
     p.blocks_done[b] = blocks_done;
     p.stepsz[b] = stepsz;
     p.inner_total[b] = inner_total;
@@ -1727,16 +1725,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
 // ------------------------------------------- host side -------------------------------------------
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-struct CoopGeom { int nxe, nye, nyh, TR, TKY, grid, d_pipe, d_fuse, fast_y, fast_x; size_t smem; };
+struct CoopGeom { int nxe, nye, nyh, TR, TKY, grid, d_fuse, fast_y, fast_x, tma_d, tma_R, tma_S, work_bytes; size_t smem; };
 
 static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   CoopGeom g;
+  const Knobs& kn = p.knobs;
   g.nxe = (p.ndim == 1) ? 1 : p.nx;
   g.nye = (p.ndim == 1) ? p.nx : p.ny;
   g.nyh = g.nye / 2 + 1;
   const int rows = p.K * g.nxe;
   // y-FFT tile: TR rows (even) -> TR/2 complex transforms, two buffers of (TR/2)*(nye+1) complex
-  const size_t tab = (size_t)kArgsBytes + kRedBytes + (size_t)24 * (g.nxe + g.nye) + 32;   // args, reduction scratch, twiddles + coefficient tables
+  const size_t tab = (size_t)kArgsBytes + kRedBytes + kBarBytes + (size_t)24 * (g.nxe + g.nye) + 32;   // args, reduction scratch, barriers, twiddles + coefficient tables
   const size_t cap = smem_cap > tab ? smem_cap - tab : 0;
   int TR = 16;
   while (TR > 2 && ((rows + TR - 1) / TR < 2 * sm_count || (size_t)TR * fft_ld(g.nye) * 16 > cap)) TR -= 2;
@@ -1747,28 +1746,45 @@ static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   const size_t smA = (size_t)TR * fft_ld(g.nye) * 16;                 // 2 buffers * TR/2 rows
   const size_t smB = (g.nxe > 1) ? (size_t)2 * TKY * fft_ld(g.nxe) * 16 : 0;
   size_t work = smA > smB ? smA : smB;
-  // staging buffers of the pipelined dual sweep: 2 stages per warp
-  const size_t smD = (size_t)kWarps * 2 * ((p.ndim == 2) ? DStage<2>::kBytes : DStage<1>::kBytes);
-  g.d_pipe = ((g.nye & 1) == 0 && smD <= cap && getenv("PDHG_DPIPE") != nullptr) ? 1 : 0;   // opt-in: measured slower (L1 shrinks)
-  if (g.d_pipe && smD > work) work = smD;
   // warp-private 256-point transforms: two padded rows per warp
   const size_t smW = (size_t)kWarps * 2 * kW256Ld * 16;
-  const bool w256 = getenv("PDHG_NO_W256") == nullptr && smW <= cap;
+  const bool w256 = !kn.no_w256 && smW <= cap;
   // (a unit is one warp's work; below ~8 units per SM the tiled path, which spreads one tile over a whole CTA, is faster)
-  const bool force = getenv("PDHG_FORCE_W256") != nullptr;
+  const bool force = kn.force_w256 != 0;
   const bool many_y = force || (rows + 3) / 4 >= 8 * sm_count, many_x = force || (p.K * g.nyh + 1) / 2 >= 8 * sm_count;
   g.fast_y = (w256 && many_y && g.nye == 256 && (p.ndim == 1 ? p.bc_x == 0 : p.bc_y == 0)) ? 1 : 0;
   g.fast_x = (w256 && many_x && g.nxe == 256 && p.ndim == 2 && p.bc_x == 0) ? 1 : 0;
   if ((g.fast_y || g.fast_x) && smW > work) work = smW;
-  // fused dual sweeps: two per pass everywhere; up to kFuseMax on the large grids, whose work area already holds the
-  // per-thread accumulator slots of sweeps 3.. (3 + 4 ndim sums each)
-  // (L2-resident blocks are barrier / latency bound: a fused pass saves them nothing and a redo costs two more grid barriers)
+  // (L2-resident blocks are barrier / latency bound: fused passes and bulk-copy pipelines save them nothing)
   const bool hbm_bound = (size_t)p.K * g.nxe * g.nye * 8 * (4 + 4 * p.ndim) > ((size_t)64 << 20);
+  // dual sweep through the TMA row pipeline: 2-D grids with even ny whose ring of >= 2 stages of (7 R + 2) rows fits
+  g.tma_d = 0; g.tma_R = 0; g.tma_S = 0;
+  size_t stage = 0;
+  if (p.ndim == 2 && (g.nye & 1) == 0 && kn.tma != 0) {
+    int R = (2 * kThreads + g.nye - 1) / g.nye;                       // rows per tile: every thread gets an item
+    if (R > 8) R = 8;
+    if (R > g.nxe) R = g.nxe;
+    if (R < 1) R = 1;
+    stage = (size_t)(7 * R + 2) * g.nye * 8;
+    int S = (int)(cap / stage);
+    if (S > 4) S = 4;
+    if (S >= 2 && (hbm_bound || kn.tma == 1)) { g.tma_d = 1; g.tma_R = R; g.tma_S = S; }
+  }
+  // fused dual sweeps: two per pass on the HBM-bound grids; more (up to kFuseMax) while the per-thread accumulator slots of
+  // sweeps 3.. (3 + 4 ndim sums each) fit the work area (next to two ring stages when the TMA pipeline runs)
   g.d_fuse = !hbm_bound ? 1 : ((g.fast_y || g.fast_x) ? kFuseMax : 2);
-  if (const char* e = getenv("PDHG_DFUSE")) g.d_fuse = atoi(e);
+  if (kn.dfuse > 0) g.d_fuse = kn.dfuse;
   if (g.d_fuse > kFuseMax) g.d_fuse = kFuseMax;
-  if (g.d_fuse < 1 || g.d_pipe) g.d_fuse = 1;
-  while (g.d_fuse > 2 && (size_t)(g.d_fuse - 2) * (3 + 4 * p.ndim) * kThreads * 8 > work) --g.d_fuse;
+  if (g.d_fuse < 1) g.d_fuse = 1;
+  auto xacc_bytes = [&](int df) { return df > 2 ? (((size_t)(df - 2) * (3 + 4 * p.ndim) * kThreads * 8 + 127) & ~(size_t)127) : (size_t)0; };
+  if (g.tma_d) {
+    while (g.d_fuse > 2 && xacc_bytes(g.d_fuse) + 2 * stage > cap) --g.d_fuse;
+    const size_t ring = xacc_bytes(g.d_fuse) + 2 * stage > (size_t)g.tma_S * stage ? xacc_bytes(g.d_fuse) + 2 * stage : (size_t)g.tma_S * stage;
+    if (ring > work) work = ring;
+  } else {
+    while (g.d_fuse > 2 && xacc_bytes(g.d_fuse) > (work > cap ? cap : work)) --g.d_fuse;
+  }
+  g.work_bytes = (int)work;
   g.smem = tab + work;
   g.grid = sm_count * kCtasPerSm;
   return g;
@@ -1832,7 +1848,8 @@ static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, 
   a.p = p;
   a.w = carve(p, ws);
   a.b = b; a.mode = mode; a.A = 2 * p.ndim;
-  a.nxe = g.nxe; a.nye = g.nye; a.nyh = g.nyh; a.TR = g.TR; a.TKY = g.TKY; a.d_pipe = g.d_pipe; a.fast_y = g.fast_y; a.fast_x = g.fast_x; a.d_fuse = g.d_fuse;
+  a.nxe = g.nxe; a.nye = g.nye; a.nyh = g.nyh; a.TR = g.TR; a.TKY = g.TKY; a.fast_y = g.fast_y; a.fast_x = g.fast_x; a.d_fuse = g.d_fuse;
+  a.tma_d = g.tma_d; a.tma_R = g.tma_R; a.tma_S = g.tma_S; a.work_bytes = g.work_bytes;
   a.has_x = (p.ndim == 2);
   if (p.ndim == 1) {
     a.dxe = 1.0; a.dye = p.dx; a.coef_xe = p.coef_x; a.coef_ye = p.coef_x; a.tw_xe = p.tw_x; a.tw_ye = p.tw_x;

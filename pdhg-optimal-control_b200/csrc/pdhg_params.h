@@ -13,6 +13,16 @@ enum : int { END_CONVERGED = 0, END_NAN = 1, END_MAXITER = 2, END_PAUSED = 3 };
 
 constexpr int kLogCols = 4;   // err1, err2, min rho_next, max rho_next
 
+// Diagnostic knobs, read from the environment ONCE per handle (pdhg_create) — never on the launch path.  None is needed in
+// normal use; the parity tests use them to force every kernel variant onto small grids.
+struct Knobs {
+  int no_w256, force_w256;   // PDHG_NO_W256 / PDHG_FORCE_W256: tiled vs warp-private 256-point transforms
+  int dfuse;                 // PDHG_DFUSE=n: max. dual sweeps fused per pass (0 = automatic)
+  int tma;                   // PDHG_TMA=0|1: TMA row pipelines off / forced wherever they are supported (-1 = automatic)
+  int no_k1;                 // PDHG_NO_K1: 1-D K = 1 problems on the generic single-CTA kernel
+  int profile;               // PDHG_PROFILE: sub-step cycle counters of the single-CTA kernel
+};
+
 // Problem + marching description for the time-block solver kernels.  One "instance" = one independent
 // HJ problem; instance b uses g/epsl/stepsz index b.  All pointers are device pointers.
 struct MarchParams {
@@ -66,6 +76,7 @@ struct MarchParams {
   int* status;                     // [B]
   int* blocks_done;                // [B]
   long long* inner_total;          // [B] total dual sweeps executed (statistics)
+  Knobs knobs;
   double* dbg_ns;                  // [16] diagnostic: clock cycles per sub-step of instance 0 (single-CTA kernel); may be null
 };
 

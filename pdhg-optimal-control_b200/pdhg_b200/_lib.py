@@ -18,7 +18,8 @@ END_CONVERGED, END_NAN, END_MAXITER, END_PAUSED = 0, 1, 2, 3
 LOG_COLS = 4
 
 EXPORTS = ("pdhg_create", "pdhg_destroy", "pdhg_last_error", "pdhg_path", "pdhg_launch_count", "pdhg_last_kernel_ms", "pdhg_phase_times", "pdhg_debug_phase", "pdhg_ext_phase", "pdhg_update_primal",
-           "pdhg_update_dual", "pdhg_solve_block", "pdhg_multi_step", "pdhg_multi_step_host")
+           "pdhg_update_dual", "pdhg_solve_block", "pdhg_multi_step", "pdhg_multi_step_host", "pdhg_multi_step_range", "pdhg_get_march_state",
+           "pdhg_set_march_state")
 
 
 class PdhgError(RuntimeError):
@@ -85,6 +86,12 @@ def load():
   lib.pdhg_solve_block.argtypes = [vp, dp, dp, dp, dp, dp, i64, i64, i64, i32, dp, dp, dp, C.POINTER(Logs), vp]
   lib.pdhg_multi_step.restype = C.c_int
   lib.pdhg_multi_step.argtypes = [vp, dp, dp, dp, i64, i32, dp, dp, dp, C.POINTER(Logs), vp]
+  lib.pdhg_multi_step_range.restype = C.c_int
+  lib.pdhg_multi_step_range.argtypes = [vp, dp, dp, dp, dp, i64, i32, i32, i32, dp, dp, dp, C.POINTER(Logs), vp]
+  lib.pdhg_get_march_state.restype = C.c_int
+  lib.pdhg_get_march_state.argtypes = [vp, dp, dp, dp, vp]
+  lib.pdhg_set_march_state.restype = C.c_int
+  lib.pdhg_set_march_state.argtypes = [vp, dp, dp, dp, vp]
   lib.pdhg_multi_step_host.restype = C.c_int
   lib.pdhg_multi_step_host.argtypes = [vp, dp, dp, dp, i64, i32, dp, dp, dp, C.POINTER(Logs)]
   _lib = lib
@@ -207,6 +214,25 @@ class Solver:
     _check(self.lib.pdhg_multi_step(self._h, g_ptr, _hptr(epsl), _hptr(stepsz), int(n_maxiter), int(print_freq),
                                     phi_ptr, rho_ptr, alp_ptr, C.byref(logs.struct), stream))
     return logs
+
+  def multi_step_range_dev(self, g_ptr, epsl, stepsz0, stepsz_cur, n_maxiter, print_freq, blk_begin, blk_end, phi_ptr, rho_ptr, alp_ptr,
+                           logs=None, stream=None):
+    """Time blocks [blk_begin, blk_end) of the march (pdhg_multi_step_range); `logs` may be passed back in to accumulate."""
+    if logs is None:
+      logs = LogBuffers(self.B, self.nblocks, self.max_rec)
+    epsl = _f64(epsl, (self.B,))
+    stepsz0 = _f64(stepsz0, (self.B,))
+    cur = None if stepsz_cur is None else _f64(stepsz_cur, (self.B,))
+    _check(self.lib.pdhg_multi_step_range(self._h, g_ptr, _hptr(epsl), _hptr(stepsz0), None if cur is None else _hptr(cur), int(n_maxiter),
+                                          int(print_freq), int(blk_begin), int(blk_end), phi_ptr, rho_ptr, alp_ptr, C.byref(logs.struct),
+                                          stream))
+    return logs
+
+  def get_march_state(self, phi_ptr, rho_ptr, alp_ptr, stream=None):
+    _check(self.lib.pdhg_get_march_state(self._h, phi_ptr, rho_ptr, alp_ptr, stream))
+
+  def set_march_state(self, phi_ptr, rho_ptr, alp_ptr, stream=None):
+    _check(self.lib.pdhg_set_march_state(self._h, phi_ptr, rho_ptr, alp_ptr, stream))
 
   def solve_block_dev(self, phi0_ptr, rho0_ptr, alp0_ptr, epsl, stepsz, n_maxiter, iter_begin, iter_pause, print_freq,
                       phi_out_ptr, rho_out_ptr, alp_out_ptr, stream=None):

@@ -51,7 +51,8 @@ def _grid(ndim, nx, ny, nt, x_period, y_period, T):
 
 def solve_HJ(ndim, n_ctrl, egno, epsl, fns_dict, nx, ny, nt, x_period, y_period, T, x_arr,
              c_on_rho, time_step_per_PDHG, stepsz_param, N_maxiter, print_freq, eps, bc, save_dir=None,
-             save_middle_dir=None, save_middle_prefix=None, C=1.0, pow=1.0, Ct=1.0, info=None):
+             save_middle_dir=None, save_middle_prefix=None, C=1.0, pow=1.0, Ct=1.0, info=None, load_middle_dir=None,
+             load_middle_prefix=None):
   """run_example.py:157-210.  `C`, `pow`, `Ct` replace the reference's reads of FLAGS inside the closures."""
   dt, period_spatial, dspatial, nspatial = _grid(ndim, nx, ny, nt, x_period, y_period, T)
   print('period_spatial: ', period_spatial)
@@ -65,7 +66,8 @@ def solve_HJ(ndim, n_ctrl, egno, epsl, fns_dict, nx, ny, nt, x_period, y_period,
   return PDHG_multi_step(fn_update_primal, fn_update_dual, fns_dict, g, x_arr, ndim, nt, nspatial, dt, dspatial, c_on_rho,
                          time_step_per_PDHG=time_step_per_PDHG, epsl=epsl, stepsz_param=stepsz_param, fv=fv, n_ctrl=n_ctrl,
                          N_maxiter=N_maxiter, print_freq=print_freq, eps=eps, save_middle_dir=save_middle_dir,
-                         save_middle_prefix=save_middle_prefix, info=info)
+                         save_middle_prefix=save_middle_prefix, load_middle_dir=load_middle_dir, load_middle_prefix=load_middle_prefix,
+                         info=info)
 
 
 def solve_HJ_batch(ndim, n_ctrl, egno, epsl, fns_dict, nx, ny, nt, x_period, y_period, T, x_arr, g,
@@ -96,7 +98,7 @@ def main(argv):
     filename_prefix = 'nt{}_nx{}_ny{}'.format(nt, nx, ny)
   else:
     raise NotImplementedError
-  if FLAGS.load:
+  if FLAGS.load or FLAGS.load_middle:
     assert FLAGS.load_timestamp != ''
     time_stamp = FLAGS.load_timestamp
   else:
@@ -108,10 +110,14 @@ def main(argv):
     results, errs_all = load_solution(save_dir, filename_prefix)
   else:
     smd, smp = (save_dir, filename_prefix) if FLAGS.save_middle else (None, None)
+    # --load_middle --load_timestamp T restarts the march from the middle file of run T (written by --save_middle) at the first
+    # unsolved time block; the reference defines the flag but never wires it (run_example.py:249-254)
+    # (same file name as the final pickle, as in the reference :293-295: an interrupted run leaves the middle list there)
+    lmd, lmp = (save_dir, filename_prefix) if FLAGS.load_middle else (None, None)
     results, errs_all = solve_HJ(ndim, n_ctrl, egno, FLAGS.epsl, fns_dict, nx, ny, nt, FLAGS.x_period, FLAGS.y_period, FLAGS.T,
                                  x_arr, FLAGS.c_on_rho, FLAGS.time_step_per_PDHG, FLAGS.stepsz_param, FLAGS.N_maxiter,
                                  FLAGS.print_freq, FLAGS.eps, bc, save_middle_dir=smd, save_middle_prefix=smp,
-                                 C=FLAGS.C, pow=FLAGS.pow, Ct=FLAGS.Ct)
+                                 C=FLAGS.C, pow=FLAGS.pow, Ct=FLAGS.Ct, load_middle_dir=lmd, load_middle_prefix=lmp)
     if FLAGS.save:
       save(save_dir, filename_prefix, (results, errs_all))
   if FLAGS.plot or FLAGS.tfboard or FLAGS.plot_traj_num_1d:

@@ -6,6 +6,7 @@ order and meaning.  Arrays may be NumPy (copied to the GPU and back) or torch CU
 reference's two lambdas (run_example.py:193-203); `PDHG_solver_oneiter` / `PDHG_multi_step` recognise them and
 run the whole loop on the GPU instead of calling them once per iteration.
 """
+import collections
 import os
 
 import numpy as np
@@ -13,7 +14,15 @@ import numpy as np
 from . import _dev, _lib
 from .set_fns import coef_tables
 
-_handles = {}
+# Handle cache: an LRU of at most PDHG_HANDLE_CACHE (default 8) `pdhg_handle`s — a handle pins its workspaces in device memory
+# (0.7 GB for the 256 x 256 x 64 space-time block), so sweeps over grids / epsl / batch sizes must not accumulate them.
+_handles = collections.OrderedDict()
+_KNOB_ENV = ("PDHG_NO_W256", "PDHG_FORCE_W256", "PDHG_DFUSE", "PDHG_TMA", "PDHG_NO_K1", "PDHG_PROFILE", "PDHG_MAX_RADIX")
+
+
+def _knob_key():
+  """The library reads its diagnostic knobs from the environment once per handle (pdhg_create), so they are part of the key."""
+  return tuple(os.environ.get(k) for k in _KNOB_ENV)
 
 
 def get_solver(fns_dict, nspatial, K, bc, dt, dspatial, c_on_rho, x_arr, C=1.0, pow=1.0, Ct=1.0, eps=1e-6, rho_alp_iters=10,
@@ -30,13 +39,18 @@ def get_solver(fns_dict, nspatial, K, bc, dt, dspatial, c_on_rho, x_arr, C=1.0, 
   coef_x, coef_y = coef_tables(fns_dict.egno, ndim, _np(x_arr))
   key = (ndim, fns_dict.egno, nx, ny, int(K), fns_dict.n_ctrl, bc if ndim == 1 else tuple(bc), float(dt), dx, dy, float(c_on_rho),
          float(C), float(pow), float(Ct), float(eps), int(rho_alp_iters), int(batch), int(nblocks), int(max_rec), device, path,
-         coef_x.tobytes(), None if coef_y is None else coef_y.tobytes())
+         coef_x.tobytes(), None if coef_y is None else coef_y.tobytes(), _knob_key())
   s = _handles.get(key)
-  if s is None:
+  if s is not None:
+    _handles.move_to_end(key)
+  else:
     s = _lib.Solver(ndim, fns_dict.egno, nx, ny, int(K), fns_dict.n_ctrl, bc, float(dt), dx, dy, float(c_on_rho), coef_x, coef_y,
                     float(C), float(pow), float(Ct), float(eps), int(rho_alp_iters), int(batch), int(nblocks), int(max_rec),
                     device, path)
     _handles[key] = s
+    cap = max(1, int(os.environ.get("PDHG_HANDLE_CACHE", "8")))
+    while len(_handles) > cap:
+      _handles.popitem(last=False)      # least recently used; destroyed (Solver.__del__) once no caller holds it any more
   return s
 
 

@@ -150,6 +150,84 @@ def _print_block_log(i, nt_PDHG, logs, b, pf):
     iters - 1, last[0], last[1], last[1]), flush=True)
 
 
+def _middle_lists(phi, rho, alp, done, K, nt_PDHG):
+  """The reference's middle-file lists (utils_pdhg_solver.py:193-199): per block phi_curr[:-1] (the last block: all of it), rho, alp."""
+  return ([phi[i * K:(i + 1) * K + (1 if i == nt_PDHG - 1 else 0)] for i in range(done)], [rho[i * K:(i + 1) * K] for i in range(done)],
+          [alp[:, i * K:(i + 1) * K] for i in range(done)])
+
+
+def _march_blockwise(s, g, nt, nt_PDHG, K, ndim, nspatial, n_ctrl, epsl, stepsz_param, N_maxiter, pf, save_dir, save_prefix, load_dir, load_prefix):
+  """One pdhg_multi_step_range launch per time block.  After every block the middle file
+      [max_iters, phi_all, rho_all, alp_all, errs_all, resume]
+  is rewritten: entries 0..4 are the reference's (solver.py:28-33), `resume` = {"phi0": the next block's warm-started phi0,
+  "stepsz_param": the step size after the fallbacks so far, "blocks_done"} is what a restart needs and the reference's file lacks
+  (it drops phi_curr[-1] of the last saved block and the current step size, which is why its load path cannot work)."""
+  from ..solver import load_middle_solution
+  t = _dev.require_cuda()
+  dev = "cuda:%d" % _dev.current_device()
+  nsp = tuple(nspatial)
+  A = 2 * ndim
+  phi = t.zeros((1, nt) + nsp, dtype=t.float64, device=dev)
+  rho = t.zeros((1, nt - 1) + nsp, dtype=t.float64, device=dev)
+  alp = t.zeros((1, A, nt - 1) + nsp + (n_ctrl,), dtype=t.float64, device=dev)
+  g_d = _dev.to_dev(np.asarray(g, dtype=np.float64).reshape((1,) + nsp) if not _dev.is_tensor(g) else g.reshape((1,) + nsp))
+  logs = _lib.LogBuffers(1, nt_PDHG, s.max_rec)
+  begin, cur = 0, float(stepsz_param)
+  if load_dir is not None:
+    mid = load_middle_solution(load_dir, load_prefix)
+    begin = len(mid[1])
+    assert begin == len(mid[2]) == len(mid[3]) == len(mid[4])
+    if begin > 0:
+      if len(mid) < 6 or not isinstance(mid[5], dict) or "phi0" not in mid[5]:
+        raise ValueError("middle file {}/{} has no resume record (written by the reference, whose load path is unwired): cannot restart "
+                         "from it".format(load_dir, load_prefix))
+      rs = mid[5]
+      assert int(rs["blocks_done"]) == begin
+      cur = float(rs["stepsz_param"])
+      for i in range(begin):      # re-install the blocks already solved
+        pb = np.asarray(mid[1][i]); nr = pb.shape[0]
+        phi[0, i * K:i * K + nr] = _dev.to_dev(pb)
+        rho[0, i * K:(i + 1) * K] = _dev.to_dev(np.asarray(mid[2][i]))
+        alp[0, :, i * K:(i + 1) * K] = _dev.to_dev(np.asarray(mid[3][i]))
+        e = np.asarray(mid[4][i], dtype=np.float64).reshape(-1, 2)
+        logs.nrec[0, i] = len(e); logs.errlog[0, i, :len(e), :2] = e
+        logs.iters[0, i] = int(rs["block_iters"][i]); logs.stepsz_used[0, i] = float(rs["stepsz_used"][i]); logs.end_reason[0, i] = int(rs["end_reason"][i])
+      rho0 = rho[0, (begin - 1) * K:begin * K].contiguous()
+      alp0 = alp[0, :, (begin - 1) * K:begin * K].contiguous()
+      phi0 = _dev.to_dev(np.asarray(rs["phi0"]))
+      s.set_march_state(phi0.data_ptr(), rho0.data_ptr(), alp0.data_ptr(), _dev.stream_ptr())
+      logs.blocks_done[0] = begin; logs.stepsz_final[0] = cur
+  kept = {k: getattr(logs, k).copy() for k in ("iters", "stepsz_used", "nrec", "errlog", "end_reason")}
+  inner = 0
+  for i in range(begin, nt_PDHG):
+    lg = s.multi_step_range_dev(g_d.data_ptr(), float(epsl), float(stepsz_param), cur, int(N_maxiter), pf, i, i + 1, phi.data_ptr(),
+                                rho.data_ptr(), alp.data_ptr(), stream=_dev.stream_ptr())
+    inner += int(lg.inner_total[0])
+    ok = int(lg.blocks_done[0]) == i + 1
+    for k in kept:
+      kept[k][0, i] = getattr(lg, k)[0, i]
+    cur = float(lg.stepsz_final[0])
+    logs.status[0] = lg.status[0]; logs.stepsz_final[0] = cur
+    if not ok:
+      break
+    logs.blocks_done[0] = i + 1
+    if save_dir is not None:
+      done = i + 1
+      phi0 = t.empty((1, K + 1) + nsp, dtype=t.float64, device=dev)
+      r0, a0 = t.empty((1, K) + nsp, dtype=t.float64, device=dev), t.empty((1, A, K) + nsp + (n_ctrl,), dtype=t.float64, device=dev)
+      s.get_march_state(phi0.data_ptr(), r0.data_ptr(), a0.data_ptr(), _dev.stream_ptr())
+      ph, rh, ah = phi[0].cpu().numpy(), rho[0].cpu().numpy(), alp[0].cpu().numpy()
+      pl, rl, al = _middle_lists(ph, rh, ah, done, K, nt_PDHG)
+      errs = [kept["errlog"][0, j, :int(kept["nrec"][0, j]), :2].copy() for j in range(done)]
+      resume = {"phi0": phi0[0].cpu().numpy(), "stepsz_param": cur, "blocks_done": done, "block_iters": kept["iters"][0, :done].tolist(),
+                "stepsz_used": kept["stepsz_used"][0, :done].tolist(), "end_reason": kept["end_reason"][0, :done].tolist()}
+      save(save_dir, save_prefix, [int(kept["iters"][0, :done].max()), pl, rl, al, errs, resume])
+  for k in kept:
+    getattr(logs, k)[...] = kept[k]
+  logs.inner_total[0] = inner
+  return phi, rho, alp, logs
+
+
 def PDHG_multi_step(fn_update_primal, fn_update_dual, fns_dict, g, x_arr,
                     ndim, nt, nspatial, dt, dspatial, c_on_rho, time_step_per_PDHG=2,
                     epsl=0.0, stepsz_param=0.9, n_ctrl=None, fv=None,
@@ -178,7 +256,17 @@ def PDHG_multi_step(fn_update_primal, fn_update_dual, fns_dict, g, x_arr,
                  rho_alp_iters=fn_update_dual.rho_alp_iters, batch=1, nblocks=nt_PDHG, max_rec=_max_rec(N_maxiter, pf))
   utils.timer.tic("time estimate")
   on_dev = _dev.is_tensor(g)
-  if on_dev:
+  save_mid = save_middle_dir is not None and save_middle_prefix is not None
+  load_mid = load_middle_dir is not None and load_middle_prefix is not None
+  if save_mid or load_mid:
+    # block-wise march (one launch per time block): the middle file is rewritten after EVERY block as in the reference
+    # (utils_pdhg_solver.py:211-212), and a march can restart from it (a working version of :139-154)
+    phi, rho, alp, logs = _march_blockwise(s, g, nt, nt_PDHG, K, ndim, nspatial, n_ctrl, epsl, stepsz_param, N_maxiter, pf,
+                                           save_middle_dir if save_mid else None, save_middle_prefix, load_middle_dir if load_mid else None,
+                                           load_middle_prefix)
+    if not on_dev:
+      phi, rho, alp = phi.cpu().numpy(), rho.cpu().numpy(), alp.cpu().numpy()
+  elif on_dev:
     t = _dev.require_cuda()
     g_d = _dev.to_dev(g)
     phi_d = t.empty((1, nt) + tuple(nspatial), dtype=t.float64, device=g_d.device)
@@ -194,6 +282,9 @@ def PDHG_multi_step(fn_update_primal, fn_update_dual, fns_dict, g, x_arr,
   sol_nan = int(logs.status[0]) == _lib.INST_SOL_NAN
   if int(logs.status[0]) == _lib.INST_LOG_OVERFLOW:
     print('warning: error log overflow, some periodic records were dropped', flush=True)
+  if done < nt_PDHG and not sol_nan:
+    raise RuntimeError("PDHG_multi_step: the march stopped after {} of {} time blocks without a NaN failure (status {})".format(
+      done, nt_PDHG, int(logs.status[0])))
   # replay of the log lines (the march itself is one kernel launch)
   step = float(stepsz_param)
   errs_all = []
@@ -222,11 +313,6 @@ def PDHG_multi_step(fn_update_primal, fn_update_dual, fns_dict, g, x_arr,
   rows = done * K + (1 if done == nt_PDHG else 0)
   phi_out, rho_out, alp_out = phi[0, :rows], rho[0, :done * K], alp[0, :, :done * K]
   results_out = [(max_iters, phi_out, rho_out, alp_out)]
-  if save_middle_dir is not None and save_middle_prefix is not None:
-    Kk = K
-    save(save_middle_dir, save_middle_prefix,
-         [max_iters, [phi_out[i * Kk:(i + 1) * Kk + (1 if i == nt_PDHG - 1 else 0)] for i in range(done)],
-          [rho_out[i * Kk:(i + 1) * Kk] for i in range(done)], [alp_out[:, i * Kk:(i + 1) * Kk] for i in range(done)], errs_all])
   print('\n\n')
   print('===========================================')
   if sol_nan:
