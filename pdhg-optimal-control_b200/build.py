@@ -11,8 +11,7 @@ SRC = [os.path.join(HERE, "csrc", f) for f in ("pdhg_api.cu", "pdhg1d_cta.cu", "
 HDR = [os.path.join(HERE, "csrc", f) for f in ("pdhg_device.cuh", "pdhg_params.h")] + \
       [os.path.join(os.path.dirname(HERE), "include", "pdhg_b200.h")]
 OUT = os.path.join(HERE, "lib", "libpdhg_b200.so")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
 
 def up_to_date():
@@ -22,20 +21,23 @@ def up_to_date():
   return all(os.path.getmtime(f) <= t for f in SRC + HDR + [os.path.abspath(__file__)])
 
 
-def build(force=False, verbose=False):
-  if not force and up_to_date():
+def build(force=False, verbose=False, defs=(), out=None):
+  """`defs` / `out`: experiment builds (extra -D macros into a differently named library, selected with PDHG_B200_LIB)."""
+  if out is None and not force and up_to_date():
     return OUT
-  os.makedirs(os.path.dirname(OUT), exist_ok=True)
+  out = out or OUT
+  os.makedirs(os.path.dirname(out), exist_ok=True)
   nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-  flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-  cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+  cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defs] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SRC
   r = subprocess.run(cmd, capture_output=True, text=True)
   if verbose or r.returncode != 0:
     sys.stderr.write(r.stdout + r.stderr)
   if r.returncode != 0:
     raise RuntimeError("nvcc failed: " + " ".join(cmd))
-  return OUT
+  return out
 
 
 if __name__ == "__main__":
-  print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+  defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+  outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+  print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defs=defs, out=os.path.join(HERE, "lib", outs[0]) if outs else None))

@@ -16,6 +16,7 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 
 #include "pdhg_params.h"
 
@@ -70,6 +71,9 @@ struct CoopArgs {
   int fast_y, fast_x; // warp-private 256-point transforms along y (phases A, C) / along x (phase B)
   int d_fuse;         // max. inner dual sweeps fused per pass while the inner loop is long (1 = off; PDHG_DFUSE=n overrides)
   double dxe, dye;
+  double r_idt, r_idx, r_idy, r_idx2, r_idy2;   // 1/dt, 1/dx, 1/dy, 1/dx^2, 1/dy^2 (IEEE divisions done once on the host)
+  int o_twy, o_cx, o_cy, o_work;               // byte offsets of the shared-memory tables and of the work area
+  float inv_nx;                                // 1/nxe for the division-free index arithmetic
   const double* coef_xe;
   const double* coef_ye;
   const double2* tw_xe;
@@ -84,13 +88,20 @@ struct CoopArgs {
   double* op_err;
 };
 
+// The argument block of the current launch lives in CONSTANT memory (copied there on the launch stream right before the launch):
+// every phase function — they are not inlined — reads launch constants as constant-bank operands (c[3][..] in SASS, usable
+// directly by DFMA / IMAD / address arithmetic), so grid constants, reciprocals, sizes and base pointers occupy no registers,
+// no shared memory and no local memory in the streaming loops.  (Round 1 kept a copy in shared memory: every use was an LDS
+// into a register, and under the 128-register cap ptxas split the dual sweep's load batch in two to make room — two exposed
+// memory latencies per item instead of one, profiles/r02_phaseD_stalls.txt.)
+__constant__ CoopArgs g_cargs;
 // All shared memory is ONE dynamic region addressed from this symbol, so that every access compiles to LDS/STS (pointers
-// stored in a struct would be generic and compile to LD/ST): [CoopArgs copy][reduction scratch][twx][twy][cx][cy][work].
+// stored in a struct would be generic and compile to LD/ST): [reduction scratch][barriers][twx][twy][cx][cy][work].
 extern __shared__ __align__(16) unsigned char g_sm[];
-constexpr int kArgsBytes = (int)((sizeof(CoopArgs) + 15) / 16 * 16);
+constexpr int kArgsBytes = 0;
 constexpr int kRedBytes = kNQ * kWarps * 8;
 constexpr int kBarBytes = 128;    // mbarriers of the TMA row pipelines: full[8], empty[8]
-__device__ __forceinline__ const CoopArgs& cargs() { return *reinterpret_cast<const CoopArgs*>(g_sm); }
+__device__ __forceinline__ const CoopArgs& cargs() { return g_cargs; }
 
 // TMA row pipelines (phase_D_tma ...): ring state kept by every thread; the mbarriers full[8], empty[8] live in shared memory
 // behind the reduction scratch and are initialised once per launch (full: 1 arrival + transaction bytes, empty: one arrival
@@ -101,17 +112,15 @@ constexpr int kPipeMaxStages = 8;
 struct Ctx {
   cg::grid_group grid;
   RowPipe pipe;
-  int o_twy, o_cx, o_cy, o_work;     // byte offsets of the tables and of the FFT / staging buffers
   int epoch;
-  float inv_nx, inv_nchunk;          // float reciprocals for division-free index math
   unsigned long long tsub[10], tl;   // diagnostic sub-phase timers (CTA 0, thread 0 only)
   __device__ __forceinline__ double* red() const { return reinterpret_cast<double*>(g_sm + kArgsBytes); }
   __device__ __forceinline__ uint64_t* bars() const { return reinterpret_cast<uint64_t*>(g_sm + kArgsBytes + kRedBytes); }
   __device__ __forceinline__ const double2* twx() const { return reinterpret_cast<const double2*>(g_sm + kArgsBytes + kRedBytes + kBarBytes); }
-  __device__ __forceinline__ const double2* twy() const { return reinterpret_cast<const double2*>(g_sm + o_twy); }
-  __device__ __forceinline__ const double* cx() const { return reinterpret_cast<const double*>(g_sm + o_cx); }
-  __device__ __forceinline__ const double* cy() const { return reinterpret_cast<const double*>(g_sm + o_cy); }
-  __device__ __forceinline__ double2* work() const { return reinterpret_cast<double2*>(g_sm + o_work); }
+  __device__ __forceinline__ const double2* twy() const { return reinterpret_cast<const double2*>(g_sm + cargs().o_twy); }
+  __device__ __forceinline__ const double* cx() const { return reinterpret_cast<const double*>(g_sm + cargs().o_cx); }
+  __device__ __forceinline__ const double* cy() const { return reinterpret_cast<const double*>(g_sm + cargs().o_cy); }
+  __device__ __forceinline__ double2* work() const { return reinterpret_cast<double2*>(g_sm + cargs().o_work); }
   __device__ __forceinline__ void tick(int slot) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       unsigned long long t;
@@ -123,16 +132,7 @@ struct Ctx {
     const CoopArgs& a = cargs();
     for (int i = 0; i < 10; ++i) tsub[i] = 0;
     tl = 0;
-    inv_nx = 1.0f / (float)a.nxe;
-    {
-      const int vw = (a.nye & 1) ? 1 : 2;
-      inv_nchunk = 1.0f / (float)(((a.nye / vw) + 31) >> 5);
-    }
-    const int o_twx = kArgsBytes + kRedBytes + kBarBytes;
-    o_twy = o_twx + 16 * a.nxe;
-    o_cx = o_twy + 16 * a.nye;
-    o_cy = o_cx + 8 * a.nxe;
-    o_work = (o_cy + 8 * a.nye + 15) / 16 * 16;
+    const int o_twx = kArgsBytes + kRedBytes + kBarBytes, o_twy = a.o_twy, o_cx = a.o_cx, o_cy = a.o_cy;
     double2* tx = reinterpret_cast<double2*>(g_sm + o_twx);
     double2* ty = reinterpret_cast<double2*>(g_sm + o_twy);
     double* px = reinterpret_cast<double*>(g_sm + o_cx);
@@ -166,6 +166,8 @@ template <typename T> __device__ __forceinline__ T* as_global(T* p) { __builtin_
 template <int VW> struct Vec { double e[VW]; };
 // Explicit global-space accesses (ld.global / st.global): the workspace pointers arrive through structs, so plain
 // dereferences compile to GENERIC LD/ST (slower address-space resolution); these compile to LDG/STG.
+#ifdef PDHG_ASM_LDST
+// round-1 style: volatile inline-asm accesses (fixed program order, "memory" clobbers on the stores)
 __device__ __forceinline__ double ldg1(const double* p) {
   double v;
   asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(__cvta_generic_to_global(p)));
@@ -182,6 +184,15 @@ __device__ __forceinline__ void stg1(double* p, double v) {
 __device__ __forceinline__ void stg2(void* p, double2 v) {
   asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(p)), "d"(v.x), "d"(v.y) : "memory");
 }
+#else
+// Plain accesses on pointers the compiler knows to be global (as_global): LDG / STG as well, but without the scheduling
+// barriers of volatile asm — no "memory" clobber that forces every shared- / local-memory resident value (the argument block,
+// the context) to be re-read after each store, and loads may be hoisted and batched freely.
+__device__ __forceinline__ double ldg1(const double* p) { return *as_global(p); }
+__device__ __forceinline__ double2 ldg2(const void* p) { return *as_global(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ void stg1(double* p, double v) { *as_global(p) = v; }
+__device__ __forceinline__ void stg2(void* p, double2 v) { *as_global(reinterpret_cast<double2*>(p)) = v; }
+#endif
 template <int VW> __device__ __forceinline__ Vec<VW> ldv(const double* p) {
   Vec<VW> r;
   if (VW == 2) { const double2 t = ldg2(p); r.e[0] = t.x; r.e[VW - 1] = t.y; }
@@ -412,7 +423,7 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
   const double* a1y = al + (size_t)(2 * ND - 2) * KN;
   const double* a2y = al + (size_t)(2 * ND - 1) * KN;
   const int tid = threadIdx.x, nth = blockDim.x;
-  const Recip rc(p.dt, a.dxe, a.dye, 1.0);
+  const Recip rc(a.r_idt, a.r_idx, a.r_idy, a.r_idx2, a.r_idy2, 1.0);
   const double c_dt = p.c_on_rho * rc.idt;
   const int ny2 = ny / VW;
   const int dlr = nth / ny2, djp = nth - dlr * ny2;
@@ -426,7 +437,7 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
 #pragma unroll
       for (int e = 0; e < VW; ++e) res.e[e] = 0.0;
       if (lr < nrows) {
-        const int r = r0 + lr, k = fast_div_exact(r, nx, c.inv_nx), i = r - k * nx;
+        const int r = r0 + lr, k = fast_div_exact(r, nx, cargs().inv_nx), i = r - k * nx;
         res = cont_item<ND, VW, EG>(c, rho, a1x, a2x, a1y, a2y, k, i, j, epsl, rc, c_dt);
       }
       double* dst = reinterpret_cast<double*>(&buf0[(size_t)(lr >> 1) * ld + fpad(j)]) + (lr & 1);
@@ -444,10 +455,10 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
       const int ky = fast_div_exact(idx, npairs, inv_np), pr = idx - ky * npairs;
       const int kym = (ky == 0) ? 0 : ny - ky;
       const double2 z1 = zf[(size_t)pr * ld + fpad(ky)], z2 = zf[(size_t)pr * ld + fpad(kym)];
-      const int ra = r0 + 2 * pr, ka = fast_div_exact(ra, nx, c.inv_nx), ia = ra - ka * nx;
+      const int ra = r0 + 2 * pr, ka = fast_div_exact(ra, nx, cargs().inv_nx), ia = ra - ka * nx;
       stg2(&ztg[((size_t)ka * nyh + ky) * nx + ia], make_double2(0.5 * (z1.x + z2.x), 0.5 * (z1.y - z2.y)));
       if (2 * pr + 1 < nrows) {
-        const int rb = ra + 1, kb = fast_div_exact(rb, nx, c.inv_nx), ib = rb - kb * nx;
+        const int rb = ra + 1, kb = fast_div_exact(rb, nx, cargs().inv_nx), ib = rb - kb * nx;
         stg2(&ztg[((size_t)kb * nyh + ky) * nx + ib], make_double2(0.5 * (z1.y + z2.y), 0.5 * (z2.x - z1.x)));
       }
     }
@@ -519,7 +530,7 @@ __device__ __noinline__ void phase_A_w256(Ctx& c, int cd, double epsl) {
   const double* a2x = al + KN;
   const double* a1y = al + (size_t)(2 * ND - 2) * KN;
   const double* a2y = al + (size_t)(2 * ND - 1) * KN;
-  const Recip rc(p.dt, a.dxe, a.dye, 1.0);
+  const Recip rc(a.r_idt, a.r_idx, a.r_idy, a.r_idx2, a.r_idy2, 1.0);
   const double c_dt = p.c_on_rho * rc.idt;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pr = lane >> 4, jj = lane & 15;
   double2* wbuf = c.work() + (size_t)warp * 2 * kW256Ld;
@@ -534,8 +545,8 @@ __device__ __noinline__ void phase_A_w256(Ctx& c, int cd, double epsl) {
     for (int pp = 0; pp < 2; ++pp) {
       const int ra = r0 + 2 * pp, rbw = ra + 1;
       const bool va = ra < rows, vb = rbw < rows;
-      const int ka = fast_div_exact(va ? ra : 0, nx, c.inv_nx), ia = (va ? ra : 0) - ka * nx;
-      const int kb = fast_div_exact(vb ? rbw : 0, nx, c.inv_nx), ib = (vb ? rbw : 0) - kb * nx;
+      const int ka = fast_div_exact(va ? ra : 0, nx, cargs().inv_nx), ia = (va ? ra : 0) - ka * nx;
+      const int kb = fast_div_exact(vb ? rbw : 0, nx, cargs().inv_nx), ib = (vb ? rbw : 0) - kb * nx;
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         const int j = 2 * lane + 64 * cc;
@@ -560,8 +571,8 @@ __device__ __noinline__ void phase_A_w256(Ctx& c, int cd, double epsl) {
     // split: Z_a[m] = (X[m] + conj X[N-m]) / 2, Z_b[m] = (X[m] - conj X[N-m]) / (2i), m = jj + 16 q <= 128
     const int ra = r0 + 2 * pr, rbw = ra + 1;
     const bool va = ra < rows, vb = rbw < rows;
-    const int ka = fast_div_exact(va ? ra : 0, nx, c.inv_nx), ia = (va ? ra : 0) - ka * nx;
-    const int kb = fast_div_exact(vb ? rbw : 0, nx, c.inv_nx), ib = (vb ? rbw : 0) - kb * nx;
+    const int ka = fast_div_exact(va ? ra : 0, nx, cargs().inv_nx), ia = (va ? ra : 0) - ka * nx;
+    const int kb = fast_div_exact(vb ? rbw : 0, nx, cargs().inv_nx), ib = (vb ? rbw : 0) - kb * nx;
     double2* za = ztg + (size_t)ka * nyh * nx + ia;
     double2* zb = ztg + (size_t)kb * nyh * nx + ib;
 #pragma unroll
@@ -639,8 +650,8 @@ __device__ __noinline__ void phase_C_w256(Ctx& c, const double* phi_prev, double
   for (int u = warp * gridDim.x + blockIdx.x; u < nunits; u += nwt) {
     const int ra = 4 * u + 2 * pr, rbw = ra + 1;
     const bool va = ra < rows, vb = rbw < rows;
-    const int ka = fast_div_exact(va ? ra : 0, nx, c.inv_nx), ia = (va ? ra : 0) - ka * nx;
-    const int kb = fast_div_exact(vb ? rbw : 0, nx, c.inv_nx), ib = (vb ? rbw : 0) - kb * nx;
+    const int ka = fast_div_exact(va ? ra : 0, nx, cargs().inv_nx), ia = (va ? ra : 0) - ka * nx;
+    const int kb = fast_div_exact(vb ? rbw : 0, nx, cargs().inv_nx), ib = (vb ? rbw : 0) - kb * nx;
     const double2* za = ztg + (size_t)ka * nyh * nx + ia;
     const double2* zb = ztg + (size_t)kb * nyh * nx + ib;
     double2 v[16];
@@ -801,7 +812,7 @@ __device__ __noinline__ void phase_B(Ctx& c) {
     const int k = u / ntile, ky0 = (u - k * ntile) * TKY;
     const int nr = min(TKY, nyh - ky0);
     for (int idx = tid; idx < nr * nx; idx += nth) {
-      const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
+      const int t = fast_div_exact(idx, nx, cargs().inv_nx), kx = idx - t * nx;
       buf0[(size_t)t * ld + fpad(kx)] = ldg2(&zt[((size_t)k * nyh + ky0 + t) * nx + kx]);
     }
     __syncthreads();
@@ -811,7 +822,7 @@ __device__ __noinline__ void phase_B(Ctx& c) {
       const double* ct = p.dct_cos;
       const int m4 = 4 * nx;
       for (int idx = tid; idx < nr * nx; idx += nth) {
-        const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
+        const int t = fast_div_exact(idx, nx, cargs().inv_nx), kx = idx - t * nx;
         double sx = 0.0, sy = 0.0;
         int m = kx % m4;                                  // index kx (2 i + 1) mod 4 nx, advanced by 2 kx per i
         for (int i = 0; i < nx; ++i) {
@@ -825,7 +836,7 @@ __device__ __noinline__ void phase_B(Ctx& c) {
       }
       __syncthreads();
       for (int idx = tid; idx < nr * nx; idx += nth) {
-        const int t = fast_div_exact(idx, nx, c.inv_nx), i = idx - t * nx;
+        const int t = fast_div_exact(idx, nx, cargs().inv_nx), i = idx - t * nx;
         const double2 y0 = buf1[(size_t)t * ld + fpad(0)];
         double sx = 0.5 * y0.x, sy = 0.5 * y0.y;
         const int step = (2 * i + 1) % m4;
@@ -845,7 +856,7 @@ __device__ __noinline__ void phase_B(Ctx& c) {
     if (!coupled) {
       double2* zo = (zf == buf0) ? buf1 : buf0;
       for (int idx = tid; idx < nr * nx; idx += nth) {
-        const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
+        const int t = fast_div_exact(idx, nx, cargs().inv_nx), kx = idx - t * nx;
         const double rd = 1.0 / (ldg1(p.diag + (size_t)kx * a.nyh_tab + a.ky_off + ky0 + t) + ((K == 1) ? ct2 : 0.0));
         const double2 v = zf[(size_t)t * ld + fpad(kx)];
         zf[(size_t)t * ld + fpad(kx)] = make_double2(v.x * rd, v.y * rd);
@@ -854,7 +865,7 @@ __device__ __noinline__ void phase_B(Ctx& c) {
       zf = fft_rows(zf, zo, a.plan_xe, ld, c.twx(), nr, -1.0);
     }
     for (int idx = tid; idx < nr * nx; idx += nth) {
-      const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
+      const int t = fast_div_exact(idx, nx, cargs().inv_nx), kx = idx - t * nx;
       stg2(&zt[((size_t)k * nyh + ky0 + t) * nx + kx], zf[(size_t)t * ld + fpad(kx)]);
     }
     __syncthreads();
@@ -872,13 +883,13 @@ __device__ __noinline__ void phase_B(Ctx& c) {
     const int k = u / ntile, ky0 = (u - k * ntile) * TKY;
     const int nr = min(TKY, nyh - ky0);
     for (int idx = tid; idx < nr * nx; idx += nth) {
-      const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
+      const int t = fast_div_exact(idx, nx, cargs().inv_nx), kx = idx - t * nx;
       buf0[(size_t)t * ld + fpad(kx)] = ldg2(&zt[((size_t)k * nyh + ky0 + t) * nx + kx]);
     }
     __syncthreads();
     double2* zu = fft_rows(buf0, buf1, a.plan_xe, ld, c.twx(), nr, -1.0);
     for (int idx = tid; idx < nr * nx; idx += nth) {
-      const int t = fast_div_exact(idx, nx, c.inv_nx), kx = idx - t * nx;
+      const int t = fast_div_exact(idx, nx, cargs().inv_nx), kx = idx - t * nx;
       stg2(&zt[((size_t)k * nyh + ky0 + t) * nx + kx], zu[(size_t)t * ld + fpad(kx)]);
     }
     __syncthreads();
@@ -910,11 +921,11 @@ __device__ __noinline__ void phase_C(Ctx& c, const double* phi_prev, double* phi
     const float inv_np = 1.0f / (float)npairs;
     for (int idx = tid; idx < npairs * nyh; idx += nth) {
       const int ky = fast_div_exact(idx, npairs, inv_np), pr = idx - ky * npairs;
-      const int ra = r0 + 2 * pr, ka = fast_div_exact(ra, nx, c.inv_nx), ia = ra - ka * nx;
+      const int ra = r0 + 2 * pr, ka = fast_div_exact(ra, nx, cargs().inv_nx), ia = ra - ka * nx;
       const double2 ua = ldg2(&ztg[((size_t)ka * nyh + ky) * nx + ia]);
       double2 ub = make_double2(0.0, 0.0);
       if (2 * pr + 1 < nrows) {
-        const int rb = ra + 1, kb = fast_div_exact(rb, nx, c.inv_nx), ib = rb - kb * nx;
+        const int rb = ra + 1, kb = fast_div_exact(rb, nx, cargs().inv_nx), ib = rb - kb * nx;
         ub = ldg2(&ztg[((size_t)kb * nyh + ky) * nx + ib]);
       }
       buf0[(size_t)pr * ld + fpad(ky)] = make_double2(ua.x - ub.y, ua.y + ub.x);
@@ -928,7 +939,7 @@ __device__ __noinline__ void phase_C(Ctx& c, const double* phi_prev, double* phi
     int lr = tid / ny2, jp = tid - lr * ny2;
     while (lr < nrows) {
       const int j = jp * VW;
-      const int r = r0 + lr, k = fast_div_exact(r, nx, c.inv_nx), i = r - k * nx;
+      const int r = r0 + lr, k = fast_div_exact(r, nx, cargs().inv_nx), i = r - k * nx;
       const size_t g = (size_t)(k + 1) * n + (size_t)i * ny + j;
       const double* zsrc = reinterpret_cast<const double*>(&zu[(size_t)(lr >> 1) * ld + fpad(j)]) + (lr & 1);
       const Vec<VW> pp = ldv<VW>(phi_prev + g);
@@ -1129,7 +1140,7 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
   const MarchParams& p = a.p;
   const int K = p.K, nx = a.nxe, ny = a.nye;
   const size_t n = (size_t)nx * ny, KN = (size_t)K * n;
-  const Recip rc(p.dt, a.dxe, a.dye, sigma);
+  const Recip rc(a.r_idt, a.r_idx, a.r_idy, a.r_idx2, a.r_idy2, 1.0 / sigma);
   const int ny2 = ny / VW;
   DualSums<NA> S;
   S.clear();
@@ -1144,7 +1155,7 @@ __device__ __noinline__ void phase_D(Ctx& c, const double* phib, const double* r
   for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += istride) {
     const int r = (items < (1LL << 24)) ? fast_div_exact((int)item, ny2, inv_ny2) : (int)(item / ny2);
     const int jp = (int)(item - (long long)r * ny2);
-    const int k = fast_div_exact(r, nx, c.inv_nx), i = r - k * nx, j = jp * VW;
+    const int k = fast_div_exact(r, nx, cargs().inv_nx), i = r - k * nx, j = jp * VW;
     const size_t row = (size_t)i * ny, g = (size_t)k * n + row + j;
     const double* pb1 = phib + (size_t)(k + 1) * n;
     const int jm = (j == 0) ? ny - 1 : j - 1, jq = (j + VW == ny) ? 0 : j + VW;
@@ -1190,7 +1201,7 @@ __device__ __noinline__ void phase_D_tma(Ctx& c, const double* phib, const doubl
   const MarchParams& p = a.p;
   const int K = p.K, nx = a.nxe, ny = a.nye;
   const size_t n = (size_t)nx * ny, KN = (size_t)K * n;
-  const Recip rc(p.dt, a.dxe, a.dye, sigma);
+  const Recip rc(a.r_idt, a.r_idx, a.r_idy, a.r_idx2, a.r_idy2, 1.0 / sigma);
   const int ny2 = ny >> 1;
   const int R = a.tma_R;
   constexpr int kAcc = DualAccLayout<NA>::kAcc;
@@ -1413,15 +1424,7 @@ __device__ void build_tables(const CoopArgs& a) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const __grid_constant__ CoopArgs a_param) {
-  // the argument block is referenced from the (non-inlined) phase functions; it lives at the start of shared memory so that
-  // it is neither spilled to a local-memory copy nor lost with every L1 invalidation of a grid sync
-  {
-    const unsigned int* src = reinterpret_cast<const unsigned int*>(&a_param);
-    unsigned int* dst = reinterpret_cast<unsigned int*>(g_sm);
-    for (int i = threadIdx.x; i < (int)(sizeof(CoopArgs) / 4); i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-  }
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel() {
   const CoopArgs& a = cargs();
   Ctx c;
   double* red = c.red();
@@ -1725,6 +1728,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel(const _
 // ------------------------------------------- host side -------------------------------------------
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+constexpr int kMaxDevices = 16;
+struct ArgsSlot { cudaEvent_t ev = nullptr; cudaStream_t stream = nullptr; bool used = false; };
+static ArgsSlot g_args_slot[kMaxDevices];
+static std::mutex g_args_mutex;
+
 struct CoopGeom { int nxe, nye, nyh, TR, TKY, grid, d_fuse, fast_y, fast_x, tma_d, tma_R, tma_S, work_bytes; size_t smem; };
 
 static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
@@ -1768,7 +1776,7 @@ static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
     stage = (size_t)(7 * R + 2) * g.nye * 8;
     int S = (int)(cap / stage);
     if (S > 4) S = 4;
-    if (S >= 2 && (hbm_bound || kn.tma == 1)) { g.tma_d = 1; g.tma_R = R; g.tma_S = S; }
+    if (S >= 2 && kn.tma == 1) { g.tma_d = 1; g.tma_R = R; g.tma_S = S; }   // opt-in: see DESIGN.md (direct loads already saturate HBM)
   }
   // fused dual sweeps: two per pass on the HBM-bound grids; more (up to kFuseMax) while the per-thread accumulator slots of
   // sweeps 3.. (3 + 4 ndim sums each) fit the work area (next to two ring stages when the TMA pipeline runs)
@@ -1862,10 +1870,29 @@ static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, 
   a.sum_lo = 0; a.sum_hi = g.nxe; a.ky_off = 0; a.nyh_tab = g.nyh;
   if (ext) apply_ext(*ext, a);
   a.op_phi_in = op_in; a.op_phi_out = op_out; a.op_step = op_step; a.op_eps = op_eps; a.op_ninner = op_ninner; a.op_err = op_err;
+  a.r_idt = 1.0 / p.dt; a.r_idx = 1.0 / a.dxe; a.r_idy = 1.0 / a.dye; a.r_idx2 = 1.0 / (a.dxe * a.dxe); a.r_idy2 = 1.0 / (a.dye * a.dye);
+  a.inv_nx = 1.0f / (float)g.nxe;
+  a.o_twy = kArgsBytes + kRedBytes + kBarBytes + 16 * g.nxe;
+  a.o_cx = a.o_twy + 16 * g.nye;
+  a.o_cy = a.o_cx + 8 * g.nxe;
+  a.o_work = (a.o_cy + 8 * g.nye + 15) / 16 * 16;
   e = cudaFuncSetAttribute(pdhg_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return e;
-  void* args[] = {&a};
-  return cudaLaunchCooperativeKernel((void*)pdhg_coop_kernel, dim3(g.grid), dim3(kThreads), args, g.smem, stream);
+  // The argument block goes to constant memory on the launch stream (ordered before the launch, after the previous kernel of
+  // that stream).  The symbol is one per device: a launch from ANOTHER stream first waits (host side) for the last launch that
+  // used it, so two handles driven from different streams serialise their launches instead of racing on it.
+  {
+    std::lock_guard<std::mutex> lock(g_args_mutex);
+    ArgsSlot& slot = g_args_slot[dev & (kMaxDevices - 1)];
+    if (slot.ev == nullptr) { e = cudaEventCreateWithFlags(&slot.ev, cudaEventDisableTiming); if (e != cudaSuccess) return e; slot.used = false; }
+    if (slot.used && slot.stream != stream) { e = cudaEventSynchronize(slot.ev); if (e != cudaSuccess) return e; }
+    e = cudaMemcpyToSymbolAsync(g_cargs, &a, sizeof(a), 0, cudaMemcpyHostToDevice, stream);   // (pageable source: staged before the call returns)
+    if (e != cudaSuccess) return e;
+    e = cudaLaunchCooperativeKernel((void*)pdhg_coop_kernel, dim3(g.grid), dim3(kThreads), nullptr, g.smem, stream);
+    if (e != cudaSuccess) return e;
+    slot.stream = stream; slot.used = true;
+    return cudaEventRecord(slot.ev, stream);
+  }
 }
 
 static cudaError_t ensure_tables(const MarchParams& p, void* ws, cudaStream_t stream, long long* launches) {

@@ -273,6 +273,9 @@ struct Recip {
   double idt, idx, idy, idx2, idy2, isig;
   __device__ __forceinline__ Recip(double dt, double dx, double dy, double sigma)
       : idt(1.0 / dt), idx(1.0 / dx), idy(1.0 / dy), idx2(1.0 / (dx * dx)), idy2(1.0 / (dy * dy)), isig(1.0 / sigma) {}
+  // from reciprocals computed once on the host (the same IEEE divisions), so that they stay constant-bank operands
+  __device__ __forceinline__ Recip(double idt_, double idx_, double idy_, double idx2_, double idy2_, double isig_)
+      : idt(idt_), idx(idx_), idy(idy_), idx2(idx2_), idy2(idy2_), isig(isig_) {}
 };
 
 // the one true division of the dual sweep: 1/(1/c_H + p) for egno 1,3 (c_H = 1), 1/p for egno 2
