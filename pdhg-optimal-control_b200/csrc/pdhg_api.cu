@@ -250,6 +250,7 @@ extern "C" int pdhg_create(const pdhg_config* cfg, const double* coef_x, const d
     h->knobs.force_w256 = getenv("PDHG_FORCE_W256") != nullptr;
     h->knobs.dfuse = env_int("PDHG_DFUSE", 0);
     h->knobs.tma = env_int("PDHG_TMA", -1);
+    h->knobs.no_bslab = getenv("PDHG_NO_BSLAB") != nullptr;
     h->knobs.no_k1 = getenv("PDHG_NO_K1") != nullptr;
     h->knobs.profile = getenv("PDHG_PROFILE") != nullptr;
     h->max_radix = env_int("PDHG_MAX_RADIX", 16);

@@ -69,6 +69,7 @@ struct CoopArgs {
   int tma_R, tma_S;
   int work_bytes;     // size of the work area (FFT buffers / accumulator slots / TMA ring)
   int fast_y, fast_x; // warp-private 256-point transforms along y (phases A, C) / along x (phase B)
+  int b_slab;         // phase B in one pass per ky-slab (phase_B_slab)
   int d_fuse;         // max. inner dual sweeps fused per pass while the inner loop is long (1 = off; PDHG_DFUSE=n overrides)
   double dxe, dye;
   double r_idt, r_idx, r_idy, r_idx2, r_idy2;   // 1/dt, 1/dx, 1/dy, 1/dx^2, 1/dy^2 (IEEE divisions done once on the host)
@@ -763,6 +764,135 @@ __device__ __forceinline__ void thomas_component(double* ztd, const double* den,
   }
 }
 
+// ===================================================================================================================
+// Phase B in ONE pass per ky-slab (nx == 256, coupled modes): a CTA owns the [K][256] complex slab of one ky.  The rows are
+// transformed along x as they arrive (global -> registers -> warp-private 256-point FFT -> shared memory), the per-mode
+// tridiagonal systems in t are solved IN SHARED MEMORY by 512 threads (one per real component of a mode, conflict-free), and
+// the rows leave through the inverse transform straight to global memory: the spectrum is read once and written once instead
+// of three times each (x-FFT pass, Thomas pass, inverse pass), and the two grid-wide barriers between the passes are gone.
+// A slab larger than the work area (K = 64: 256 KB) is processed in nchunk balanced k-chunks: forward elimination chunk by
+// chunk (the eliminated rows of all but the last chunk are parked in their own global rows), back substitution from the last
+// chunk down (the parked rows are re-read by the Thomas threads themselves, fully coalesced).  Same butterflies, same
+// recurrences (thomas_component) => bit-identical to the three-pass version.
+// The transform's 16 x 16 exchange runs inside the row's own (unpadded) shared-memory slot with an XOR swizzle
+// (element 16 J + Q at 16 J + (Q ^ J)): conflict-free for the 16-byte accesses of a quarter warp, no scratch rows.
+// ===================================================================================================================
+template <bool INV>
+__device__ __forceinline__ void wfft256_first_sw(double2 (&v)[16], double2* row, int jj) {
+  Dft<16, INV>::run(v);                                       // outputs q -> element 16 jj + q
+  __syncwarp();                                               // every lane holds its inputs in registers: the slot is free
+#pragma unroll
+  for (int q = 0; q < 16; ++q) row[16 * jj + (q ^ jj)] = v[q];
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < 16; ++t) v[t] = row[16 * t + (jj ^ t)];  // element jj + 16 t
+  __syncwarp();                                               // all exchange reads done before the slot is overwritten
+}
+
+__device__ __noinline__ void phase_B_slab(Ctx& c) {
+  const CoopArgs& a = cargs();
+  const MarchParams& p = a.p;
+  const int K = p.K, nyh = a.nyh;
+  constexpr int nx = 256;
+  const double ct2 = p.Ct_over_dt2;
+  double2* zt = as_global(a.w.zt);
+  const double* den = as_global(a.w.den);
+  const double* tu = as_global(a.w.tu);
+  const size_t modes = (size_t)nyh * nx;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pr = lane >> 4, jj = lane & 15;
+  const int Hmax = a.work_bytes / (nx * 16);                   // row slots in the work area; chunks use at most Hmax - 1 of them when
+  const int Hcap = (Hmax > 2) ? Hmax - 1 : Hmax;              // a chunk can have an odd row count (the idle half-warp's scratch slot)
+  const int nchunk = (K + Hcap - 1) / Hcap, H = (K + nchunk - 1) / nchunk;
+  double2* S = c.work();
+  double* Sd = reinterpret_cast<double*>(S);
+  const int pmask = (a.mode == MODE_PHASE) ? a.dbg_pass : 7;
+  if (!(pmask & 1)) return;
+  for (int ky = blockIdx.x; ky < nyh; ky += gridDim.x) {
+    const size_t mrow = (size_t)ky * nx;                       // first mode of this slab in the [K][modes] tables
+    const double* dn_t = den + mrow + (tid >> 1);
+    const double* tu_t = tu + mrow + (tid >> 1);
+    double bp = 0.0;
+    // ---- forward: x-FFT of the chunk's rows into shared memory, then forward elimination over its k ----
+    for (int ch = 0; ch < nchunk; ++ch) {
+      const int k0 = ch * H, nr = min(H, K - k0);
+      for (int r0 = 2 * warp; r0 < nr; r0 += 2 * kWarps) {      // a warp takes two rows; with an odd count its second half idles
+        const int r = r0 + pr;                                 // (all 32 lanes stay in the loop: the exchange uses __syncwarp)
+        const bool valid = r < nr;
+        double2* g = zt + ((size_t)(k0 + (valid ? r : r0)) * nyh + ky) * nx + jj;
+        double2 v[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t] = valid ? ldg2(g + 16 * t) : make_double2(0.0, 0.0);
+        double2* row = S + (size_t)(valid ? r : Hmax - 1) * nx;   // an idle half scribbles over the (unused) last slot
+        wfft256_first_sw<false>(v, row, jj);
+        wfft256_second<false>(v, jj, c.twx());
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) row[jj + 16 * q] = v[q];
+        }
+      }
+      __syncthreads();
+      {
+        // thread tid = real component tid & 1 of mode kx = tid >> 1; rows k0 .. k0 + nr - 1   (thomas_component's forward loop)
+        int r = 0;
+        for (; r + 8 <= nr; r += 8) {
+          double dnv[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dnv[q] = ldg1(dn_t + (size_t)(k0 + r + q) * modes);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { bp = (Sd[(size_t)(r + q) * (2 * nx) + tid] + ct2 * bp) * dnv[q]; Sd[(size_t)(r + q) * (2 * nx) + tid] = bp; }
+        }
+        for (; r < nr; ++r) { bp = (Sd[(size_t)r * (2 * nx) + tid] + ct2 * bp) * ldg1(dn_t + (size_t)(k0 + r) * modes); Sd[(size_t)r * (2 * nx) + tid] = bp; }
+      }
+      if (ch < nchunk - 1) {
+        // park the eliminated rows in their own global rows (coalesced: a row is 512 consecutive doubles)
+        double* zd = reinterpret_cast<double*>(zt);
+        for (int r = 0; r < nr; ++r) stg1(zd + (((size_t)(k0 + r) * nyh + ky) * nx) * 2 + tid, Sd[(size_t)r * (2 * nx) + tid]);
+        __syncthreads();
+      }
+    }
+    // ---- backward: substitution from the last row down, inverse x-FFT chunk by chunk ----
+    double xs = bp;                                            // x[K-1] = b'[K-1]
+    for (int ch = nchunk - 1; ch >= 0; --ch) {
+      const int k0 = ch * H, nr = min(H, K - k0);
+      const bool last = (ch == nchunk - 1);
+      const double* zd = reinterpret_cast<const double*>(zt);
+      int r = last ? nr - 2 : nr - 1;                          // the very last row is already solved (and sits in S)
+      for (; r - 7 >= 0; r -= 8) {
+        double tv[8], bv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          tv[q] = ldg1(tu_t + (size_t)(k0 + r - q) * modes);
+          bv[q] = last ? Sd[(size_t)(r - q) * (2 * nx) + tid] : ldg1(zd + (((size_t)(k0 + r - q) * nyh + ky) * nx) * 2 + tid);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { xs = bv[q] - tv[q] * xs; Sd[(size_t)(r - q) * (2 * nx) + tid] = xs; }
+      }
+      for (; r >= 0; --r) {
+        const double bv = last ? Sd[(size_t)r * (2 * nx) + tid] : ldg1(zd + (((size_t)(k0 + r) * nyh + ky) * nx) * 2 + tid);
+        xs = bv - ldg1(tu_t + (size_t)(k0 + r) * modes) * xs;
+        Sd[(size_t)r * (2 * nx) + tid] = xs;
+      }
+      __syncthreads();
+      for (int r0 = 2 * warp; r0 < nr; r0 += 2 * kWarps) {
+        const int rr = r0 + pr;
+        const bool valid = rr < nr;
+        double2* row = S + (size_t)(valid ? rr : Hmax - 1) * nx;
+        double2 v[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t] = valid ? row[jj + 16 * t] : make_double2(0.0, 0.0);
+        wfft256_first_sw<true>(v, row, jj);
+        wfft256_second<true>(v, jj, c.twx());
+        if (valid) {
+          double2* g = zt + ((size_t)(k0 + rr) * nyh + ky) * nx + jj;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) stg2(g + 16 * q, v[q]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // ---- phase B: x-FFT, t-solve per mode, inverse x-FFT (in place on zt) ----
 __device__ __noinline__ void phase_B(Ctx& c) {
   const CoopArgs& a = cargs();
@@ -797,6 +927,7 @@ __device__ __noinline__ void phase_B(Ctx& c) {
   const int pmask = (a.mode == MODE_PHASE) ? a.dbg_pass : 7;
   if (a.fast_x) {
     if (!coupled) { if (pmask & 1) phase_B_w256<0>(c, zt, K * nyh); return; }
+    if (a.b_slab) { phase_B_slab(c); return; }
     if (pmask & 1) phase_B_w256<1>(c, zt, K * nyh);
     c.grid.sync();
     c.tick(3);
@@ -1838,7 +1969,7 @@ static void apply_ext(const ExtPhaseDesc& e, CoopArgs& a) {
   if (e.alp_out) a.w.alp[1] = e.alp_out;
   if (e.zt) a.w.zt = static_cast<double2*>(e.zt);
   a.sum_lo = e.sum_lo; a.sum_hi = e.sum_hi;
-  if (e.nyh_override > 0) { a.nyh = e.nyh_override; a.ky_off = e.ky_off; a.nyh_tab = e.nyh_tab; }
+  if (e.nyh_override > 0) { a.nyh = e.nyh_override; a.ky_off = e.ky_off; a.nyh_tab = e.nyh_tab; a.b_slab = 0; }
 }
 
 static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, const double* op_in, double* op_out,
@@ -1857,6 +1988,7 @@ static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, 
   a.w = carve(p, ws);
   a.b = b; a.mode = mode; a.A = 2 * p.ndim;
   a.nxe = g.nxe; a.nye = g.nye; a.nyh = g.nyh; a.TR = g.TR; a.TKY = g.TKY; a.fast_y = g.fast_y; a.fast_x = g.fast_x; a.d_fuse = g.d_fuse;
+  a.b_slab = (g.fast_x && kThreads == 512 && p.K > 1 && !p.knobs.no_bslab) ? 1 : 0;
   a.tma_d = g.tma_d; a.tma_R = g.tma_R; a.tma_S = g.tma_S; a.work_bytes = g.work_bytes;
   a.has_x = (p.ndim == 2);
   if (p.ndim == 1) {

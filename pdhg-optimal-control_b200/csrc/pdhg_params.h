@@ -19,6 +19,7 @@ struct Knobs {
   int no_w256, force_w256;   // PDHG_NO_W256 / PDHG_FORCE_W256: tiled vs warp-private 256-point transforms
   int dfuse;                 // PDHG_DFUSE=n: max. dual sweeps fused per pass (0 = automatic)
   int tma;                   // PDHG_TMA=0|1: TMA row pipelines off / forced wherever they are supported (-1 = automatic)
+  int no_bslab;              // PDHG_NO_BSLAB: phase B in three grid-wide passes instead of one pass per ky-slab
   int no_k1;                 // PDHG_NO_K1: 1-D K = 1 problems on the generic single-CTA kernel
   int profile;               // PDHG_PROFILE: sub-step cycle counters of the single-CTA kernel
 };

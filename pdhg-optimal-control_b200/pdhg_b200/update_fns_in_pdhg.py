@@ -17,7 +17,7 @@ from .set_fns import coef_tables
 # Handle cache: an LRU of at most PDHG_HANDLE_CACHE (default 8) `pdhg_handle`s — a handle pins its workspaces in device memory
 # (0.7 GB for the 256 x 256 x 64 space-time block), so sweeps over grids / epsl / batch sizes must not accumulate them.
 _handles = collections.OrderedDict()
-_KNOB_ENV = ("PDHG_NO_W256", "PDHG_FORCE_W256", "PDHG_DFUSE", "PDHG_TMA", "PDHG_NO_K1", "PDHG_PROFILE", "PDHG_MAX_RADIX")
+_KNOB_ENV = ("PDHG_NO_W256", "PDHG_FORCE_W256", "PDHG_DFUSE", "PDHG_TMA", "PDHG_NO_BSLAB", "PDHG_NO_K1", "PDHG_PROFILE", "PDHG_MAX_RADIX")
 
 
 def _knob_key():

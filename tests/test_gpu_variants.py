@@ -13,7 +13,7 @@ from helpers import TOL, golden, golden_names, quiet, relmax
 
 pytestmark = pytest.mark.gpu
 
-KNOBS = ("PDHG_FORCE_PATH", "PDHG_FORCE_W256", "PDHG_NO_W256", "PDHG_DFUSE", "PDHG_TMA", "PDHG_NO_K1")
+KNOBS = ("PDHG_FORCE_PATH", "PDHG_FORCE_W256", "PDHG_NO_W256", "PDHG_DFUSE", "PDHG_TMA", "PDHG_NO_K1", "PDHG_NO_BSLAB")
 
 
 @pytest.fixture(scope="module")
@@ -114,6 +114,19 @@ def test_fused_dual_sweeps_cold_start_bitwise_and_vs_oracle(pk, K, tma):
     for x, y in zip(r[0][0][1:], res_o[0][1:]):
       assert relmax(x, y) < TOL
     assert relmax(r[1][0], errs_o[0]) < 1e-7
+
+
+@pytest.mark.parametrize("K,ny", [(3, 256), (35, 64), (40, 32), (64, 16), (77, 8)])
+def test_single_pass_phase_B_equals_three_pass_bitwise(pk, K, ny):
+  """Phase B in one pass per ky-slab (x-FFT -> Thomas in shared memory -> inverse x-FFT; K = 40, 64, 77 need 2 or 3 k-chunks)
+  runs the same butterflies and recurrences as the three grid-wide passes: bit-identical iterates."""
+  nx, nt, T = 256, K + 1, K / 64.0
+  a = _solve(pk, 1, 2, nx, ny, nt, T, nt, 0.01, 0.05, 12, PDHG_FORCE_W256=1)
+  b = _solve(pk, 1, 2, nx, ny, nt, T, nt, 0.01, 0.05, 12, PDHG_FORCE_W256=1, PDHG_NO_BSLAB=1)
+  assert a[2]["block_iters"] == b[2]["block_iters"] and a[2]["n_inner"] == b[2]["n_inner"]
+  for x, y in zip(a[0][0][1:], b[0][0][1:]):
+    assert np.array_equal(np.asarray(x), np.asarray(y))
+  assert np.array_equal(np.concatenate(a[1]), np.concatenate(b[1]))
 
 
 def test_headline_geometry_first_iterations_vs_oracle(pk):
