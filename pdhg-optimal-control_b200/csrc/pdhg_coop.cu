@@ -37,6 +37,15 @@ constexpr int kThreads = PDHG_COOP_THREADS;
 constexpr int kCtasPerSm = PDHG_COOP_CTAS_PER_SM;
 constexpr int kWarps = kThreads / 32;
 
+// diagnostic sub-phase timers share slots 0..2 between phase A and the single-pass phase B: -DPDHG_TICKS_B shows B's
+#ifdef PDHG_TICKS_B
+#define PDHG_TICK_A(s)
+#define PDHG_TICK_B(s) c.tick(s)
+#else
+#define PDHG_TICK_A(s) c.tick(s)
+#define PDHG_TICK_B(s)
+#endif
+
 struct CoopWs {
   double* phi[2];     // ping-pong phi [(K+1) n]
   double* phib;       // phi_bar [(K+1) n]
@@ -565,10 +574,12 @@ __device__ __noinline__ void phase_A_w256(Ctx& c, int cd, double epsl) {
       }
     }
     __syncwarp();
+    PDHG_TICK_A(0);
     double2 v[16];
 #pragma unroll
     for (int t = 0; t < 16; ++t) v[t] = rb[jj + 17 * t];
     wfft256<false>(v, rb, jj, c.twy());
+    PDHG_TICK_A(1);
     // split: Z_a[m] = (X[m] + conj X[N-m]) / 2, Z_b[m] = (X[m] - conj X[N-m]) / (2i), m = jj + 16 q <= 128
     const int ra = r0 + 2 * pr, rbw = ra + 1;
     const bool va = ra < rows, vb = rbw < rows;
@@ -593,6 +604,7 @@ __device__ __noinline__ void phase_A_w256(Ctx& c, int cd, double epsl) {
       if (va) stg2(za + mo, make_double2(z1.x, 0.0));
       if (vb) stg2(zb + mo, make_double2(z1.y, 0.0));
     }
+    PDHG_TICK_A(2);
   }
 }
 
@@ -664,6 +676,7 @@ __device__ __noinline__ void phase_C_w256(Ctx& c, const double* phi_prev, double
       const double2 ub = vb ? ldg2(zb + (size_t)mm * nx) : make_double2(0.0, 0.0);
       v[t] = lo ? make_double2(ua.x - ub.y, ua.y + ub.x) : make_double2(ua.x + ub.y, ub.x - ua.y);
     }
+    c.tick(6);
     wfft256_first<true>(v, rb, jj);
     // phi_prev of row a is requested before the second butterfly pass, that of row b before row a's update: the latency of
     // both hides behind arithmetic (the loads are volatile asm, so they stay where they are written)
@@ -672,6 +685,7 @@ __device__ __noinline__ void phase_C_w256(Ctx& c, const double* phi_prev, double
 #pragma unroll
     for (int q = 0; q < 16; ++q) pa[q] = va ? ldg1(phi_prev + ga + 16 * q) : 0.0;
     wfft256_second<true>(v, jj, c.twy());
+    c.tick(7);
     if (va) {
       const bool acc = (ia >= a.sum_lo && ia < a.sum_hi);
 #pragma unroll
@@ -698,6 +712,7 @@ __device__ __noinline__ void phase_C_w256(Ctx& c, const double* phi_prev, double
         if (phib) stg1(phib + gb + 16 * q, 2 * pn - pp);
       }
     }
+    c.tick(8);
   }
   const double sums[3] = {s_d, s_p, s_n};
   cta_partials<3>(c, sums, 16);
@@ -797,24 +812,38 @@ __device__ __noinline__ void phase_B_slab(Ctx& c) {
   const double ct2 = p.Ct_over_dt2;
   double2* zt = as_global(a.w.zt);
   const double* den = as_global(a.w.den);
-  const double* tu = as_global(a.w.tu);
   const size_t modes = (size_t)nyh * nx;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pr = lane >> 4, jj = lane & 15;
-  const int Hmax = a.work_bytes / (nx * 16);                   // row slots in the work area; chunks use at most Hmax - 1 of them when
-  const int Hcap = (Hmax > 2) ? Hmax - 1 : Hmax;              // a chunk can have an odd row count (the idle half-warp's scratch slot)
-  const int nchunk = (K + Hcap - 1) / Hcap, H = (K + nchunk - 1) / nchunk;
+  // work area = Hmax row slots of the spectrum (4 KB each) + Hmax rows of reciprocal pivots (2 KB each, staged by TMA);
+  // a chunk with an odd row count leaves one slot free (the idle half-warp's scratch slot)
+  const int Hmax = a.work_bytes / (nx * 24);
+  int nchunk = (K + Hmax - 1) / Hmax, H = (K + nchunk - 1) / nchunk;
+  if (((H & 1) || ((K - (nchunk - 1) * H) & 1)) && H == Hmax) {   // an odd chunk needs the spare slot
+    nchunk = (K + Hmax - 2) / (Hmax - 1); H = (K + nchunk - 1) / nchunk;
+  }
   double2* S = c.work();
   double* Sd = reinterpret_cast<double*>(S);
+  double* dsm = Sd + (size_t)Hmax * nx * 2;                    // [Hmax][256] reciprocal pivots of the current chunk
+  uint64_t* bar = c.bars();                                    // full[0] of the pipeline barriers (1 arrival + transaction bytes)
   const int pmask = (a.mode == MODE_PHASE) ? a.dbg_pass : 7;
   if (!(pmask & 1)) return;
+  fence_proxy_async_smem();                                    // generic-proxy accesses of the work area before the bulk copies
+  __syncthreads();
+  // the chunk's rows of the reciprocal-pivot table (2 KB each, contiguous over kx) -> shared memory, asynchronously
+  auto stage_pivots = [&](int ky, int k0, int nr) {
+    if (warp == 0) {
+      if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)nr * nx * 8u);
+      __syncwarp();
+      for (int r = lane; r < nr; r += 32) bulk_g2s(dsm + (size_t)r * nx, den + (size_t)(k0 + r) * modes + (size_t)ky * nx, nx * 8u, bar);
+    }
+  };
+  auto wait_pivots = [&]() { mbar_wait(bar, c.pipe.par_full & 1u); c.pipe.par_full ^= 1u; };
   for (int ky = blockIdx.x; ky < nyh; ky += gridDim.x) {
-    const size_t mrow = (size_t)ky * nx;                       // first mode of this slab in the [K][modes] tables
-    const double* dn_t = den + mrow + (tid >> 1);
-    const double* tu_t = tu + mrow + (tid >> 1);
     double bp = 0.0;
     // ---- forward: x-FFT of the chunk's rows into shared memory, then forward elimination over its k ----
     for (int ch = 0; ch < nchunk; ++ch) {
       const int k0 = ch * H, nr = min(H, K - k0);
+      stage_pivots(ky, k0, nr);                                // lands while the rows are loaded and transformed
       for (int r0 = 2 * warp; r0 < nr; r0 += 2 * kWarps) {      // a warp takes two rows; with an odd count its second half idles
         const int r = r0 + pr;                                 // (all 32 lanes stay in the loop: the exchange uses __syncwarp)
         const bool valid = r < nr;
@@ -831,48 +860,52 @@ __device__ __noinline__ void phase_B_slab(Ctx& c) {
         }
       }
       __syncthreads();
-      {
-        // thread tid = real component tid & 1 of mode kx = tid >> 1; rows k0 .. k0 + nr - 1   (thomas_component's forward loop)
-        int r = 0;
-        for (; r + 8 <= nr; r += 8) {
-          double dnv[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) dnv[q] = ldg1(dn_t + (size_t)(k0 + r + q) * modes);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) { bp = (Sd[(size_t)(r + q) * (2 * nx) + tid] + ct2 * bp) * dnv[q]; Sd[(size_t)(r + q) * (2 * nx) + tid] = bp; }
-        }
-        for (; r < nr; ++r) { bp = (Sd[(size_t)r * (2 * nx) + tid] + ct2 * bp) * ldg1(dn_t + (size_t)(k0 + r) * modes); Sd[(size_t)r * (2 * nx) + tid] = bp; }
-      }
+      PDHG_TICK_B(0);
+      wait_pivots();
+      // thread tid = real component tid & 1 of mode kx = tid >> 1; rows k0 .. k0 + nr - 1   (thomas_component's forward loop)
+      const double* dn_t = dsm + (tid >> 1);
+#pragma unroll 4
+      for (int r = 0; r < nr; ++r) { bp = (Sd[(size_t)r * (2 * nx) + tid] + ct2 * bp) * dn_t[(size_t)r * nx]; Sd[(size_t)r * (2 * nx) + tid] = bp; }
+      PDHG_TICK_B(1);
       if (ch < nchunk - 1) {
         // park the eliminated rows in their own global rows (coalesced: a row is 512 consecutive doubles)
         double* zd = reinterpret_cast<double*>(zt);
         for (int r = 0; r < nr; ++r) stg1(zd + (((size_t)(k0 + r) * nyh + ky) * nx) * 2 + tid, Sd[(size_t)r * (2 * nx) + tid]);
+        fence_proxy_async_smem();
         __syncthreads();
+        PDHG_TICK_B(2);
       }
     }
-    // ---- backward: substitution from the last row down, inverse x-FFT chunk by chunk ----
+    // ---- backward: substitution from the last row down (super-diagonal of U: tu[k] = -ct2 * rpivot[k], as build_tables
+    // defines it), inverse x-FFT chunk by chunk ----
     double xs = bp;                                            // x[K-1] = b'[K-1]
     for (int ch = nchunk - 1; ch >= 0; --ch) {
       const int k0 = ch * H, nr = min(H, K - k0);
       const bool last = (ch == nchunk - 1);
       const double* zd = reinterpret_cast<const double*>(zt);
+      const double* dn_t = dsm + (tid >> 1);
       int r = last ? nr - 2 : nr - 1;                          // the very last row is already solved (and sits in S)
-      for (; r - 7 >= 0; r -= 8) {
-        double tv[8], bv[8];
+      if (last) {
+#pragma unroll 4
+        for (; r >= 0; --r) { xs = Sd[(size_t)r * (2 * nx) + tid] - (-ct2 * dn_t[(size_t)r * nx]) * xs; Sd[(size_t)r * (2 * nx) + tid] = xs; }
+      } else {
+        wait_pivots();                                         // staged while the previous chunk's rows were transformed back
+        for (; r - 7 >= 0; r -= 8) {                           // the parked rows come back from global memory, 8 loads deep
+          double bv[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          tv[q] = ldg1(tu_t + (size_t)(k0 + r - q) * modes);
-          bv[q] = last ? Sd[(size_t)(r - q) * (2 * nx) + tid] : ldg1(zd + (((size_t)(k0 + r - q) * nyh + ky) * nx) * 2 + tid);
+          for (int q = 0; q < 8; ++q) bv[q] = ldg1(zd + (((size_t)(k0 + r - q) * nyh + ky) * nx) * 2 + tid);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { xs = bv[q] - (-ct2 * dn_t[(size_t)(r - q) * nx]) * xs; Sd[(size_t)(r - q) * (2 * nx) + tid] = xs; }
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { xs = bv[q] - tv[q] * xs; Sd[(size_t)(r - q) * (2 * nx) + tid] = xs; }
+        for (; r >= 0; --r) {
+          xs = ldg1(zd + (((size_t)(k0 + r) * nyh + ky) * nx) * 2 + tid) - (-ct2 * dn_t[(size_t)r * nx]) * xs;
+          Sd[(size_t)r * (2 * nx) + tid] = xs;
+        }
       }
-      for (; r >= 0; --r) {
-        const double bv = last ? Sd[(size_t)r * (2 * nx) + tid] : ldg1(zd + (((size_t)(k0 + r) * nyh + ky) * nx) * 2 + tid);
-        xs = bv - ldg1(tu_t + (size_t)(k0 + r) * modes) * xs;
-        Sd[(size_t)r * (2 * nx) + tid] = xs;
-      }
+      fence_proxy_async_smem();
       __syncthreads();
+      PDHG_TICK_B(3);
+      if (ch > 0) stage_pivots(ky, (ch - 1) * H, min(H, K - (ch - 1) * H));   // the next (earlier) chunk's pivots, under the inverse transforms
       for (int r0 = 2 * warp; r0 < nr; r0 += 2 * kWarps) {
         const int rr = r0 + pr;
         const bool valid = rr < nr;
@@ -889,6 +922,7 @@ __device__ __noinline__ void phase_B_slab(Ctx& c) {
         }
       }
       __syncthreads();
+      PDHG_TICK_B(4);
     }
   }
 }
@@ -1548,8 +1582,11 @@ __device__ void build_tables(const CoopArgs& a) {
     for (int k = 0; k < K; ++k) {
       const double dk = dg + ((k == K - 1) ? ct2 : 2.0 * ct2);
       const double den = (k == 0) ? dk : dk + ct2 * tprev;
-      tprev = ((k == K - 1) ? 0.0 : -ct2) / den;
-      a.w.den[(size_t)k * modes + m] = 1.0 / den;      // reciprocal pivot
+      const double rden = 1.0 / den;                   // reciprocal pivot
+      // modified super-diagonal du / pivot through the reciprocal (<= 1 ulp from the division of utils_precond.py:21): the
+      // single-pass phase B then needs only the reciprocal-pivot table and forms this product on the fly
+      tprev = (k == K - 1) ? 0.0 : -ct2 * rden;
+      a.w.den[(size_t)k * modes + m] = rden;
       a.w.tu[(size_t)k * modes + m] = tprev;
     }
   }
