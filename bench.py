@@ -9,8 +9,9 @@ Headline workload (BASELINE.json configs[2], the config the north-star's HBM-roo
   N = 64*256*256 = 4.19 M points, ~300 MB of state: larger than the 126 MB L2, i.e. HBM-bound).
 Other workloads (secondary lines in the "others" key or via --workload): cfg3_tsp2 (reference default tsp=2,
 L2-resident), cfg1 (README example, full solve), cfg2 (1-D viscous 640x161 at a stable step size).
-N > 1: the path does not shard a single grid without a collective ("replicas only") — every rank runs
-one independent instance of the workload (an epsl sweep), no data-path collective; value = sum over ranks.
+N > 1 (torchrun): the sharded workload of the north-star — BASELINE configs[3], 4096 independent 1-D instances, first 8 time
+blocks, contiguous instance ranges per rank, NO data-path collective (strong scaling; logs all-gathered over NCCL) — plus, under
+"others", the x-slab decomposition of the configs[4] grid over the same ranks and the same instances on one GPU.
 """
 import argparse
 import contextlib
@@ -210,40 +211,55 @@ def oracle_iterations(pb, n_iters):
 
 
 def cpu_baseline(pb, budget_s=20.0):
+  """NumPy oracle (the CPU port of the reference) on the SAME iterations as the main line (the first outer iterations of block 0
+  from the cold initial state), at least 3 of them, 1 process: NumPy's elementwise kernels and pocketfft are single-threaded."""
   t1, it1 = oracle_iterations(pb, 1)
-  n = int(max(1, min(200, budget_s / max(t1, 1e-6))))
-  t, it = (t1, it1) if n == 1 else oracle_iterations(pb, n)
+  n = int(max(3, min(200, budget_s / max(t1, 1e-6))))
+  t, it = oracle_iterations(pb, n)
   return {"value": it * pb["N"] / t, "unit": "grid-point updates/s", "cores": 1, "kind": "port",
-          "iters_per_s": it / t, "sample": "the first %d outer PDHG iteration(s) of block 0 of the same workload from the cold initial state, NumPy fp64 oracle, 1 process "
-          "(JAX is not installable here, so the reference's own JAX-CPU path cannot be timed)" % it}
+          "iters_per_s": it / t, "sample": "the first %d outer PDHG iterations of block 0 of the same workload from the cold initial state (the main line's "
+          "window), NumPy fp64 oracle, 1 process (JAX is not installable here, so the reference's own JAX-CPU path cannot be timed)" % it}
+
+
+def cfg4_inputs(B, nx=1024):
+  rng = np.random.default_rng(0)
+  A_, th, u = rng.uniform(0.5, 1.5, 4096)[:B], rng.uniform(0, 2 * np.pi, 4096)[:B], rng.uniform(0, 1, 4096)[:B]
+  x = np.linspace(0.0, 2.0, num=nx, endpoint=False)
+  g = A_[:, None] * np.sin(np.pi * x[None, :] + th[:, None])
+  return g, 0.002 * u
+
+
+def _cfg4_cpu_worker(args):
+  """One oracle process: marches instance `b` of configs[3] through `nblk` time blocks; returns (iterations, seconds)."""
+  b, nblk, nx, nt_full = args
+  from oracle import pdhg_numpy as orc
+  g, epsl = cfg4_inputs(b + 1, nx)
+  x_arr, bc, n_ctrl = orc.make_grid(1, 1, nx, 1, 2.0, 2.0)
+  info = {}
+  t0 = time.perf_counter()
+  orc.solve_HJ(1, n_ctrl, 1, float(epsl[b]), orc.set_up_example_fns(1, 1, 0), nx, 1, nblk + 1, 2.0, 2.0, nblk / (nt_full - 1.0), x_arr, 70.0, 2, 0.1,
+               1000000, 10 ** 9, 1e-6, bc, g=g[b:b + 1], info=info)
+  return int(sum(info["block_iters"])), time.perf_counter() - t0
+
+
+def cpu_baseline_batched(nblk=1, nx=1024, nt_full=257):
+  """Leg (ii) of SURVEY.md section 8(d): os.cpu_count() oracle processes, each marching ONE configs[3] instance through its first
+  time block (independent instances need no communication, so this is what the CPU can do with all its cores)."""
+  import multiprocessing as mp
+  cores = os.cpu_count() or 1
+  ctx = mp.get_context("spawn")
+  t0 = time.perf_counter()
+  with ctx.Pool(cores) as pool:
+    res = pool.map(_cfg4_cpu_worker, [(b, nblk, nx, nt_full) for b in range(cores)])
+  wall = time.perf_counter() - t0
+  its = sum(r[0] for r in res)
+  busy = max(r[1] for r in res)
+  return {"value": its * nx / busy, "unit": "grid-point updates/s", "cores": cores, "kind": "port", "pdhg_iters_per_s": its / busy, "busy_s": busy,
+          "sample": "%d processes (os.cpu_count()), one BASELINE configs[3] instance each (nx=%d), first %d of %d time blocks to the reference's "
+                    "stopping rule: %d iterations in %.1f s (slowest process; %.1f s incl. process start-up)" % (cores, nx, nblk, nt_full - 1, its, busy, wall)}
 
 
 SPINUP = {"cfg3_tsp65": 600}    # untimed iterations before the timed region (steady-state inner-sweep count)
-
-
-def batched_sample(device):
-  """BASELINE configs[3] sample: independent 1-D instances (nx=1024, tsp=2, varied initial data / epsl) marched for the first
-  4 of the 256 time blocks, one CTA per instance, 4 CTAs per SM's worth of instances."""
-  import torch
-  from pdhg_b200 import run_example as rx, set_fns
-  B, nx, nt_full, nblk = 592, 1024, 257, 4
-  rng = np.random.default_rng(0)
-  A_, th, u = rng.uniform(0.5, 1.5, 4096)[:B], rng.uniform(0, 2 * np.pi, 4096)[:B], rng.uniform(0, 1, 4096)[:B]
-  x_arr = rx.make_x_arr(1, nx, 1, 2.0, 2.0)
-  g = A_[:, None] * np.sin(np.pi * x_arr[0, :, 0][None, :] + th[:, None])
-  with contextlib.redirect_stdout(io.StringIO()):
-    fns = set_fns.set_up_example_fns(1, 1, 0)
-  T = nblk / (nt_full - 1)
-  run = lambda: rx.solve_HJ_batch(1, 1, 1, 0.002 * u, fns, nx, 1, nblk + 1, 2.0, 2.0, T, x_arr, g, 70.0, 2, 0.1, 1000000, 10000, 1e-6, 0,
-                                  device=device)
-  run()
-  t0 = time.perf_counter()
-  phi, rho, alp, logs = run()
-  t = time.perf_counter() - t0
-  its = int(logs.iters.sum())
-  return {"workload": "BASELINE configs[3] sample: %d of 4096 instances, nx=1024, first %d of 256 blocks, host buffers in/out" % (B, nblk),
-          "instances": B, "total_iters": its, "seconds": t, "pdhg_iters_per_s": its / t, "grid_point_updates_per_s": its * nx / t,
-          "all_converged": bool((logs.status == 0).all())}
 
 
 def time_to_tol(name, device, nblocks=None):
@@ -274,6 +290,117 @@ def secondary(name, device, iters):
           "algorithmic_GBps": by / (r["kernel_ms"] * 1e-3) / 1e9, "kernel_path": r["path"]}
 
 
+def src_hash():
+  """sha256 (first 16 hex digits) of the kernel sources: stamps ncu-derived numbers so that stale ones are never reported."""
+  import hashlib
+  h = hashlib.sha256()
+  d = os.path.join(ROOT, "pdhg-optimal-control_b200", "csrc")
+  for fn in sorted(os.listdir(d)):
+    if fn.endswith((".cu", ".cuh", ".h")):
+      h.update(open(os.path.join(d, fn), "rb").read())
+  return h.hexdigest()[:16]
+
+
+def measured_traffic(tag):
+  """DRAM bytes per outer iteration from the committed ncu capture profiles/traffic_<tag>.json — only when that capture was
+  taken with exactly these kernel sources (src_hash); otherwise None (never a stale constant)."""
+  f = os.path.join(ROOT, "profiles", "traffic_%s.json" % tag)
+  try:
+    d = json.load(open(f))
+    if d.get("src_hash") == src_hash():
+      return float(d["dram_bytes_per_iter"])
+  except Exception:
+    pass
+  return None
+
+
+def roofline_of(pb, r, peak, peak_src, tag):
+  n_in = r["n_inner"] / max(r["iters"], 1)
+  by = algorithmic_bytes_per_iter(pb["ndim"], pb["K"], pb["nx"], pb["ny"], n_in) * r["iters"]
+  ach = by / (r["kernel_ms"] * 1e-3) / 1e9
+  tr = measured_traffic(tag)
+  out = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+         "traffic": tr * r["iters"] if tr else None,
+         "dram_frac": (tr * r["iters"] / (r["kernel_ms"] * 1e-3) / 1e9 / peak) if tr else None,
+         "kernel": "pdhg_coop_kernel" if r["path"] == 2 else "pdhg1d_cta_kernel", "kernel_ms": r["kernel_ms"], "launches": r["launches"],
+         "iters": r["iters"], "inner_sweeps_per_iter": n_in, "ms_per_iter": r["kernel_ms"] / max(r["iters"], 1),
+         "algorithmic_bytes_per_launch": by, "peak_source": peak_src,
+         "traffic_source": ("ncu dram__bytes_read+write of this window, profiles/traffic_%s.json (same kernel sources: src_hash %s)" % (tag, src_hash()))
+                           if tr else "no ncu capture of these kernel sources committed (profiles/traffic_%s.json is stale or absent)" % tag}
+  return out
+
+
+def cfg4_sharded(rank, world, local, dist, nblk=8, B=4096):
+  """BASELINE configs[3]: 4096 independent 1-D instances (nx=1024, varied initial data / epsl), first `nblk` of the 256 time blocks,
+  sharded over the ranks with NO data-path collective (pdhg_b200/sharding.py -> solve_HJ_batch per rank, one CTA per instance);
+  the per-instance logs are all-gathered at the end.  Strong scaling: the same B instances at every N."""
+  import torch
+  from pdhg_b200 import run_example as rx, set_fns, sharding
+  nx, nt_full = 1024, 257
+  g, epsl = cfg4_inputs(B, nx)
+  x_arr = rx.make_x_arr(1, nx, 1, 2.0, 2.0)
+  with contextlib.redirect_stdout(io.StringIO()):
+    fns = set_fns.set_up_example_fns(1, 1, 0)
+  T = nblk / (nt_full - 1.0)
+  kms = {}
+
+  def solve(gs, es, ss):
+    info = {}
+    out = rx.solve_HJ_batch(1, 1, 1, es, fns, nx, 1, nblk + 1, 2.0, 2.0, T, x_arr, gs, 70.0, 2, ss, 1000000, 10 ** 9, 1e-6, 0, device=local,
+                            info=info)
+    kms["ms"] = info["kernel_ms"]
+    return out
+  run = lambda: sharding.solve_batch_sharded(solve, g, epsl, 0.1, rank, world, dist if world > 1 else None)
+  # warm-up on a small slice (handle creation, allocations), then the timed sharded solve
+  sharding.solve_batch_sharded(solve, g[:max(world * 4, 8)], epsl[:max(world * 4, 8)], 0.1, rank, world, dist if world > 1 else None)
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  b, e, phi, rho, alp, logs = run()
+  torch.cuda.synchronize()
+  t_local = time.perf_counter() - t0
+  t = torch.tensor([t_local, kms["ms"] * 1e-3], dtype=torch.float64, device="cuda")
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  its = float(np.sum(logs["total_iters"]))
+  return {"workload": "BASELINE configs[3]: %d independent 1-D instances (egno=1, nx=1024, nt=257, varied initial data / epsl), first %d of 256 time "
+                      "blocks each to the reference's stopping rule, sharded over %d GPU(s) with no data-path collective" % (B, nblk, world),
+          "instances": B, "blocks": nblk, "total_iters": its, "all_converged": bool(np.all(logs["status"] == 0)),
+          "seconds_e2e": float(t[0]), "seconds_kernel": float(t[1]), "pdhg_iters_per_s": its / float(t[0]),
+          "value_device": its * nx / float(t[1]), "value_e2e": its * nx / float(t[0]),
+          "h2d_bytes": int(g[b:e].nbytes), "d2h_bytes": int(phi.nbytes + rho.nbytes + alp.nbytes), "my_instances": [int(b), int(e)]}
+
+
+def slab_line(rank, world, local, dist, nx=2048, iters=30):
+  """BASELINE configs[4] grid (2048 x 2048, epsl = 0.1, tsp = 2, stepsz 5e-4, block 0) x-slab decomposed over the ranks (NCCL halo
+  exchange, all-to-all transposes, all-reduce of the error sums; pdhg_b200/slab.py): iterations/s of a fixed iteration budget."""
+  import torch
+  from pdhg_b200 import run_example as rx, set_fns as sf, slab
+  ny, T, epsl, stepsz = nx, 1.0 / 256, 0.1, 5e-4
+  x_arr = rx.make_x_arr(2, nx, ny, 2.0, 2.0)
+  with contextlib.redirect_stdout(io.StringIO()):
+    fns = sf.set_up_example_fns(1, 2, 0)
+  g = sf.set_up_J(1, 2, (2.0, 2.0))(x_arr)[0]
+  R = slab.SlabRank(rank, world, fns, nx, ny, T, (2.0 / nx, 2.0 / ny), 70.0, x_arr, device=local)
+  grp = slab.DistGroup(R, dist)
+  out = {}
+  for label, n in (("warm", 3), ("timed", iters)):
+    slab.init_block(grp, g, 70.0)
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = slab.solve_block_slab(grp, epsl, stepsz, n)
+    torch.cuda.synchronize(); dist.barrier()
+    out[label] = (time.perf_counter() - t0, res)
+  t = torch.tensor([out["timed"][0]], dtype=torch.float64, device="cuda")
+  dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  it_s, n_in = out["timed"][1][0], out["timed"][1][4]
+  return {"workload": "BASELINE configs[4] grid: egno=1 ndim=2 epsl=0.1 nx=ny=%d tsp=2 stepsz_param=5e-4, block 0, x-slab decomposed over %d GPUs "
+                      "(NCCL: 2 halo exchanges, 2 all-to-all transposes, 1 all-reduce per dual pass and iteration)" % (nx, world),
+          "iters": it_s, "inner_sweeps_per_iter": n_in / max(it_s, 1), "seconds": float(t[0]), "pdhg_iters_per_s": it_s / float(t[0]),
+          "grid_point_updates_per_s": it_s * nx * ny / float(t[0]), "ms_per_iter": float(t[0]) / max(it_s, 1) * 1e3}
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
@@ -291,21 +418,31 @@ def main():
   if a.impl == "reference":
     if rank != 0:
       return 0
+    if world > 1:
+      # the N-rank line of our arm is the sharded configs[3] workload: the CPU can run it on all its cores (independent instances)
+      cb = cpu_baseline_batched(nblk=1)
+      line = {"impl": "reference", "metric": "grid_point_updates_per_s", "value": cb["value"], "unit": "grid-point updates/s", "n_gpus": a.gpus,
+              "steps": 1, "requested_steps": a.steps, "warmup": 0, "ms_per_step": cb["busy_s"] * 1e3, "higher_is_better": True, "scaling": "strong",
+              "vs_baseline": None, "dtype": "f64", "data": "synthetic", "pdhg_iters_per_s": cb["pdhg_iters_per_s"],
+              "config": {"workload": "BASELINE configs[3]: independent 1-D instances (egno=1, nx=1024, nt=257, varied initial data / epsl) to the "
+                                     "reference's stopping rule; CPU sample: one instance per core, first time block"},
+              "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "grid-point updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+      print(json.dumps(line))
+      return 0
     pb = make_problem_cpu(a.workload)
-    t1, _ = oracle_iterations(pb, 1)
-    for _ in range(min(warm, 3) - 1):
-      oracle_iterations(pb, 1)
+    t1, _ = oracle_iterations(pb, 1)          # warm-up (also sizes the sample)
+    # the steps this arm can finish within ~150 s; `steps` in the line is what was actually timed
     n = int(max(1, min(a.steps, 150.0 / max(t1, 1e-6))))
     t, it = oracle_iterations(pb, n)
     val = it * pb["N"] / t
-    cores = 1
     line = {"impl": "reference", "metric": "grid_point_updates_per_s", "value": val, "unit": "grid-point updates/s", "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": t / it * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps": it, "requested_steps": a.steps, "warmup": 1, "ms_per_step": t / it * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "pdhg_iters_per_s": it / t,
-            "config": {"workload": DESCR[a.workload], "timed_steps": it},
-            "cpu_baseline": {"value": val, "unit": "grid-point updates/s", "cores": cores, "kind": "port",
-                             "sample": "%d of the requested %d outer PDHG iterations (block 0, same grid), NumPy fp64 oracle port of the "
-                                       "reference, 1 process; the reference's JAX path cannot be installed in this image" % (it, a.steps)},
+            "config": {"workload": DESCR[a.workload]},
+            "cpu_baseline": {"value": val, "unit": "grid-point updates/s", "cores": 1, "kind": "port",
+                             "sample": "the first %d outer PDHG iterations of block 0 from the cold initial state (the window our arm times; %d were "
+                                       "requested, %d fit the time budget), NumPy fp64 oracle port of the reference, 1 process; the reference's JAX path "
+                                       "cannot be installed in this image" % (it, a.steps, it)},
             "e2e": {"value": val, "unit": "grid-point updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -314,112 +451,117 @@ def main():
   import torch.distributed as dist
   if not torch.cuda.is_available():
     raise SystemExit("bench.py needs a CUDA device; the product path has no CPU fallback")
-  barrier = None
+  peak, peak_src = measured_peak_gbs()
+
   if world > 1:
+    # ---- N ranks: the sharded workload of the north-star (configs[3], independent instances, no collective); strong scaling ----
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    barrier = lambda: (dist.barrier(), torch.cuda.synchronize())
-  pb = make_problem(a.workload)
-  sampler = ClockSampler(local) if rank == 0 else None
-  # every rank: one independent instance (an epsl sweep: rank r uses epsl + 1e-3*r), no data-path collective
-  # headline window: iterations [W, W+K) of the solve from its cold initial state — the same window the reference arm and the
-  # cpu_baseline can afford on a CPU.  The steady state of the same solve (1 inner sweep / iteration) is reported separately.
-  r = run_ours_block(pb, a.steps, warm, local, epsl_shift=1e-3 * rank, sampler=sampler, barrier=barrier, spinup=0)
-  ms = r["ms"]
-  iters = r["iters"]
-  # end to end through the public API (host state in, host state out) on every rank; whole-job value = all iterations / max time
-  if barrier:
-    barrier()
-  e2e = run_ours_e2e(pb, a.steps, local, r["state"])
-  if world > 1:
-    t = torch.tensor([ms, float(iters), r["kernel_ms"], e2e["s"], float(e2e["iters"])], dtype=torch.float64, device="cuda")
-    tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    ms, total_iters = float(tmax[0]), float(tsum[1])
-    e2e_s, e2e_iters = float(tmax[3]), float(tsum[4])
-  else:
-    total_iters = float(iters)
-    e2e_s, e2e_iters = e2e["s"], float(e2e["iters"])
-  if rank != 0:
-    if world > 1:
-      dist.destroy_process_group()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+      sampler.start()
+    sh = cfg4_sharded(rank, world, local, dist)
+    clocks = sampler.stop() if sampler else None
+    others = {}
+    if not a.no_others:
+      try:
+        others["cfg5_slab"] = slab_line(rank, world, local, dist)
+      except Exception as ex:
+        others["cfg5_slab"] = {"error": repr(ex)}
+      dist.barrier()
+      if rank == 0:
+        try:      # the same instances on ONE GPU in this very run: the base of the strong-scaling curve
+          others["cfg4_one_gpu"] = cfg4_sharded(0, 1, local, None)
+        except Exception as ex:
+          others["cfg4_one_gpu"] = {"error": repr(ex)}
+      dist.barrier()
+    if rank == 0:
+      line = {"metric": "grid_point_updates_per_s", "value": sh["value_device"], "unit": "grid-point updates/s", "n_gpus": world, "steps": a.steps,
+              "warmup": a.warmup, "ms_per_step": sh["seconds_kernel"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+              "dtype": "f64", "data": "synthetic", "pdhg_iters_per_s": sh["total_iters"] / sh["seconds_kernel"],
+              "config": {"workload": sh["workload"], "parallelism": "instances sharded x%d (contiguous ranges, no data-path collective; logs all-gathered)" % world,
+                         "step": "ONE step = the whole sharded solve (%d instances x %d time blocks = %.3g PDHG iterations); --steps / --warmup do not "
+                                 "apply: the workload runs to the reference's own stopping rule" % (sh["instances"], sh["blocks"], sh["total_iters"]),
+                         "l2": "state lives in shared memory / registers (one CTA per instance): HBM is touched once per time block",
+                         "kernel_path": "single-CTA K=1 register-resident kernel (pdhg1d_k1_kernel)"},
+              "gpu_launches": 2 * world, "clocks": clocks, "all_converged": sh["all_converged"],
+              "e2e": {"value": sh["value_e2e"], "unit": "grid-point updates/s", "h2d_bytes_per_step": sh["h2d_bytes"] * world,
+                      "d2h_bytes_per_step": sh["d2h_bytes"] * world, "seconds": sh["seconds_e2e"],
+                      "call": "sharding.solve_batch_sharded -> run_example.solve_HJ_batch with host arrays in / out on every rank (H2D of g, march, D2H of "
+                              "phi / rho / alp of all blocks), barrier + max over ranks"},
+              "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+                           "note": "latency-bound regime by construction (state never leaves the SM, SURVEY.md section 8d); the HBM roofline line is the "
+                                   "N = 1 run on BASELINE configs[2]"},
+              "others": others}
+      print(json.dumps(line))
+    dist.destroy_process_group()
     return 0
+
+  # ---- one GPU: BASELINE configs[2] with time_step_per_PDHG = 65 ----
+  pb = make_problem(a.workload)
+  sampler = ClockSampler(local)
+  # main window = iterations [W, W + K) of the solve from its cold initial state — the same iterations the reference arm and the
+  # cpu_baseline time on the CPU (they cannot afford the ~600 iterations to the steady state), so value / e2e compare like with like
+  r = run_ours_block(pb, a.steps, warm, local, sampler=sampler, spinup=0)
+  ms, iters = r["ms"], r["iters"]
+  e2e = run_ours_e2e(pb, a.steps, local, r["state"])
   N = pb["N"]
-  value = total_iters * N / (ms * 1e-3)
-  n_in = r["n_inner"] / max(iters, 1)
-  by_launch = algorithmic_bytes_per_iter(pb["ndim"], pb["K"], pb["nx"], pb["ny"], n_in) * iters
-  peak, peak_src = measured_peak_gbs()
-  achieved = by_launch / (r["kernel_ms"] * 1e-3) / 1e9
-  traffic = None
-  tf = os.path.join(ROOT, "profiles", "traffic_%s.json" % a.workload)          # steady-state ncu capture
-  tfc = os.path.join(ROOT, "profiles", "traffic_%s_cold.json" % a.workload)    # cold-window ncu capture
-  if os.path.exists(tfc):
-    try:
-      traffic = json.load(open(tfc))["dram_bytes_per_iter"] * iters
-    except Exception:
-      traffic = None
-  line = {"metric": "grid_point_updates_per_s", "value": value, "unit": "grid-point updates/s", "n_gpus": world, "steps": a.steps,
+  value = iters * N / (ms * 1e-3)
+  line = {"metric": "grid_point_updates_per_s", "value": value, "unit": "grid-point updates/s", "n_gpus": 1, "steps": a.steps,
           "warmup": a.warmup, "ms_per_step": ms / max(iters, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-          "dtype": "f64", "data": "synthetic", "pdhg_iters_per_s": total_iters / (ms * 1e-3), "iters_timed": iters,
-          "inner_sweeps_per_iter": n_in, "end_reason": r["end_reason"],
+          "dtype": "f64", "data": "synthetic", "pdhg_iters_per_s": iters / (ms * 1e-3), "iters_timed": iters,
+          "inner_sweeps_per_iter": r["n_inner"] / max(iters, 1), "end_reason": r["end_reason"],
           "config": {"workload": DESCR[a.workload], "grid_points_per_iter": N, "stepsz_param": pb["stepsz"],
-                     "timed_region": "iterations %d..%d of block 0 from the cold initial state (inner dual sweeps/iteration in this "
-                                     "window: see inner_sweeps_per_iter; the solve settles at 1 after ~500 iterations: steady_state)"
-                                     % (r["begin"], r["begin"] + iters),
-                     "parallelism": "replicas x%d (independent instances, no collective)" % world,
+                     "timed_region": "iterations %d..%d of block 0 from the cold initial state (up to 10 inner dual sweeps per iteration there: "
+                                     "inner_sweeps_per_iter); the roofline object is the STEADY state of the same solve (1 sweep per iteration, > 95 %% of a "
+                                     "real solve), measured in this run" % (r["begin"], r["begin"] + iters),
+                     "parallelism": "one GPU",
                      "l2": "state ~%.0f MB > 126 MB L2 (inputs larger than L2, no flush needed)" % (N * 8 * 14 / 1e6)
                            if N * 8 * 14 > 126e6 else "state fits L2 (L2-resident regime; no flush: the iteration re-reads its own state)",
                      "kernel_path": "cooperative multi-CTA" if r["path"] == 2 else "single-CTA smem"},
-          "gpu_launches": r["launches"], "clocks": r["clocks"],
-          "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                       "kernel": "pdhg_coop_kernel" if r["path"] == 2 else "pdhg1d_cta_kernel", "kernel_ms": r["kernel_ms"],
-                       "algorithmic_bytes_per_launch": by_launch, "peak_source": peak_src}}
-  if e2e:
-    line["e2e"] = {"value": e2e_iters * N / e2e_s, "unit": "grid-point updates/s", "h2d_bytes_per_step": e2e["h2d"] / max(e2e["iters"], 1),
-                   "d2h_bytes_per_step": e2e["d2h"] / max(e2e["iters"], 1), "call": "PDHG_solver_oneiter(native callables, NumPy state in pinned host memory) -> NumPy: "
-                   "H2D phi/rho/alp, %d iterations, D2H phi/rho/alp (per rank; value = all ranks' iterations / max time)" % e2e["iters"], "seconds": e2e_s}
-  if world == 1:
-    spin = SPINUP.get(a.workload, 0)
-    if spin:
-      k2 = max(20, min(a.steps, 200))
-      r2 = run_ours_block(pb, k2, warm, local, spinup=spin)
-      n2 = r2["n_inner"] / max(r2["iters"], 1)
-      by2 = algorithmic_bytes_per_iter(pb["ndim"], pb["K"], pb["nx"], pb["ny"], n2) * r2["iters"]
-      ach2 = by2 / (r2["kernel_ms"] * 1e-3) / 1e9
-      tr2 = None
-      if os.path.exists(tf):
+          "gpu_launches": r["launches"], "clocks": r["clocks"]}
+  line["e2e"] = {"value": e2e["iters"] * N / e2e["s"], "unit": "grid-point updates/s", "h2d_bytes_per_step": e2e["h2d"] / max(e2e["iters"], 1),
+                 "d2h_bytes_per_step": e2e["d2h"] / max(e2e["iters"], 1), "seconds": e2e["s"],
+                 "call": "PDHG_solver_oneiter(native callables, NumPy state in pinned host memory) -> NumPy: H2D phi/rho/alp, %d iterations, D2H "
+                         "phi/rho/alp into pooled pinned memory (the transfers of the ~0.5 GB state bound this number at small step counts)" % e2e["iters"]}
+  spin = SPINUP.get(a.workload, 0)
+  cold_rf = roofline_of(pb, r, peak, peak_src, a.workload + "_cold")
+  if spin:
+    r2 = run_ours_block(pb, max(100, min(a.steps, 400)), warm, local, spinup=spin)     # (>= 100 iterations: the launch's state copy-in/out amortised)
+    rf = roofline_of(pb, r2, peak, peak_src, a.workload)
+    rf["window"] = "steady state: iterations %d..%d of the same solve (1 inner sweep per iteration)" % (r2["begin"], r2["begin"] + r2["iters"])
+    rf["value"] = r2["iters"] * N / (r2["ms"] * 1e-3)
+    rf["phase_us_per_iter"] = {k: round(v / max(r2["iters"], 1) * 1e3, 1) for k, v in r2["solver"].phase_times_ms().items() if k[0].isupper()}
+    line["roofline"] = rf
+    cold_rf["window"] = "the main line's cold window (fused dual passes move fewer bytes than the sweep-by-sweep algorithmic count: see dram_frac)"
+    line["roofline_cold_window"] = cold_rf
+  else:
+    line["roofline"] = cold_rf
+  line["cpu_baseline"] = cpu_baseline(pb)
+  if not a.no_others:
+    others = {}
+    for nm, its in (("cfg3_tsp2", 2000), ("cfg2", 20000), ("cfg1", 3000), ("cfg5_tsp2", 100)):
+      if nm != a.workload:
         try:
-          tr2 = json.load(open(tf))["dram_bytes_per_iter"] * r2["iters"]
-        except Exception:
-          tr2 = None
-      line["steady_state"] = {"timed_region": "iterations %d..%d of the same solve" % (r2["begin"], r2["begin"] + r2["iters"]),
-                              "value": r2["iters"] * N / (r2["ms"] * 1e-3), "unit": "grid-point updates/s", "ms_per_step": r2["ms"] / max(r2["iters"], 1),
-                              "pdhg_iters_per_s": r2["iters"] / (r2["ms"] * 1e-3), "inner_sweeps_per_iter": n2,
-                              "roofline": {"bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak, "traffic": tr2,
-                                           "kernel_ms": r2["kernel_ms"], "algorithmic_bytes_per_launch": by2}}
-    line["cpu_baseline"] = cpu_baseline(pb)
-    if not a.no_others:
-      others = {}
-      for nm, its in (("cfg3_tsp2", 2000), ("cfg2", 20000), ("cfg1", 3000), ("cfg5_tsp2", 100)):
-        if nm != a.workload:
-          try:
-            others[nm] = secondary(nm, local, its)
-          except Exception as ex:   # secondary lines never break the headline
-            others[nm] = {"error": repr(ex)}
-      for nm, nb in (("cfg1", None), ("cfg3_tsp2", 3)):
-        try:
-          others["time_to_tol_" + nm] = time_to_tol(nm, local, nb)
-        except Exception as ex:
-          others["time_to_tol_" + nm] = {"error": repr(ex)}
+          others[nm] = secondary(nm, local, its)
+        except Exception as ex:   # secondary lines never break the headline
+          others[nm] = {"error": repr(ex)}
+    for nm, nb in (("cfg1", None), ("cfg3_tsp2", 3)):
       try:
-        others["cfg4_sample"] = batched_sample(local)
+        others["time_to_tol_" + nm] = time_to_tol(nm, local, nb)
       except Exception as ex:
-        others["cfg4_sample"] = {"error": repr(ex)}
-      line["others"] = others
+        others["time_to_tol_" + nm] = {"error": repr(ex)}
+    try:
+      others["cfg4_one_gpu"] = cfg4_sharded(0, 1, local, None)
+    except Exception as ex:
+      others["cfg4_one_gpu"] = {"error": repr(ex)}
+    try:
+      others["cfg4_cpu_baseline_all_cores"] = cpu_baseline_batched(nblk=1)
+    except Exception as ex:
+      others["cfg4_cpu_baseline_all_cores"] = {"error": repr(ex)}
+    line["others"] = others
   print(json.dumps(line))
-  if world > 1:
-    dist.destroy_process_group()
   return 0
 
 

@@ -72,7 +72,7 @@ def solve_HJ(ndim, n_ctrl, egno, epsl, fns_dict, nx, ny, nt, x_period, y_period,
 
 def solve_HJ_batch(ndim, n_ctrl, egno, epsl, fns_dict, nx, ny, nt, x_period, y_period, T, x_arr, g,
                    c_on_rho, time_step_per_PDHG, stepsz_param, N_maxiter, print_freq, eps, bc,
-                   C=1.0, pow=1.0, Ct=1.0, device=0, path=0):
+                   C=1.0, pow=1.0, Ct=1.0, device=0, path=0, info=None):
   """Extension for sweeps: B independent instances (initial data g[B,...], epsl[B], stepsz_param[B]) solved by ONE
   launch, one CTA (or CTA group) per instance; no collective.  Returns (phi[B,nt,..], rho, alp, logs)."""
   dt, _, dspatial, nspatial = _grid(ndim, nx, ny, nt, x_period, y_period, T)
@@ -82,7 +82,10 @@ def solve_HJ_batch(ndim, n_ctrl, egno, epsl, fns_dict, nx, ny, nt, x_period, y_p
   assert (nt - 1) % K == 0
   s = get_solver(fns_dict, nspatial, K, bc, dt, dspatial, c_on_rho, x_arr, C=C, pow=pow, Ct=Ct, eps=eps, batch=B,
                  nblocks=(nt - 1) // K, max_rec=_max_rec(N_maxiter, print_freq), device=device, path=path)
-  return s.multi_step_host(g, epsl, stepsz_param, N_maxiter, print_freq)
+  out = s.multi_step_host(g, epsl, stepsz_param, N_maxiter, print_freq)
+  if info is not None:
+    info.update(kernel_ms=s.last_kernel_ms, path=s.path, launches=s.launch_count)
+  return out
 
 
 def main(argv):

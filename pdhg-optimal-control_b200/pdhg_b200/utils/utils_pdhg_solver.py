@@ -43,9 +43,19 @@ def PDHG_solver_oneiter(fn_update_primal, fn_update_dual, fns_dict, phi0, rho0, 
                  rho_alp_iters=fn_update_dual.rho_alp_iters, max_rec=_max_rec(N_maxiter, pf) if not snapshots else 4)
   phi = _dev.to_dev(phi0)
   rho = _dev.to_dev(rho0)
-  alp = t.stack([_dev.to_dev(a) for a in alp0], dim=0).contiguous()
+  if _dev.is_tensor(alp0[0]):
+    alp = t.stack([_dev.to_dev(a) for a in alp0], dim=0).contiguous()
+  else:   # host arrays go straight into their slice of the stacked device array (no second pass over 4 x the state)
+    alp = t.empty((len(alp0),) + tuple(alp0[0].shape), dtype=t.float64, device=phi.device)
+    for j, a_ in enumerate(alp0):
+      alp[j].copy_(t.from_numpy(np.ascontiguousarray(np.asarray(a_, dtype=np.float64))), non_blocking=True)
   out = lambda d, like: _dev.like_input(d, like)
-  unstack = lambda a: tuple(out(a[j], alp0[0]) for j in range(a.shape[0]))
+
+  def unstack(a):
+    if _dev.is_tensor(alp0[0]):
+      return tuple(a[j] for j in range(a.shape[0]))
+    h = _dev.to_host([a])[0]             # one pinned copy of the stacked array; the tuple entries are views of it
+    return tuple(h[j] for j in range(h.shape[0]))
   results_all, error_all = [], []
   i = 0
   reason = _lib.END_MAXITER
