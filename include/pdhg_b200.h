@@ -183,6 +183,21 @@ int pdhg_multi_step_host(pdhg_handle* h, const double* g_host, const double* eps
                          int64_t n_maxiter, int32_t print_freq, double* phi_all_host, double* rho_all_host,
                          double* alp_all_host, pdhg_logs* logs);
 
+/* Closed-loop trajectories under the computed feedback control (run_example.py:18-155, compute_traj_1d / compute_traj_2d):
+ * Euler-Maruyama  x_{k+1} = x_k + f(alp(x_k, t_k), x_k) dt_k + sqrt(2 epsl dt_k) z_k  for n_sample independent initial points, one
+ * launch, one thread per sample.  All pointers are device pointers:
+ *   alp      1-D: [2][nt-1][nx] (the reference passes alp[..., 0]);  2-D: [4][nt-1][nx][ny][n_ctrl] (the solver's returned layout,
+ *            time already reversed by the caller as in run_example.py:356)
+ *   x_nodes  [nx] ascending grid of the x axis (1-D: already reduced mod x_period and sorted, as numpy.interp does), y_nodes [ny]
+ *   t_arr    [nt];  noise [nt-1][n_sample][ndim] standard normal draws (required iff epsl > 0; host-seeded, numpy.random order)
+ *   x_init   [n_sample] (1-D) or [n_sample][2];  traj_x [nt][n_sample](x2),  traj_alp [nt-1][n_sample][n_ctrl]
+ * nearest = 0: linear interpolation (numpy.interp with period / scipy interpn on the periodically extended or edge-clamped
+ * grid), 1: nearest grid value (egno 2, run_example.py:349-350).  bc 0 periodic, 1 edge-clamped (Neumann, egno 3 x axis). */
+int pdhg_compute_traj(int32_t ndim, int32_t egno, int32_t n_ctrl, int32_t nx, int32_t ny, int32_t nt, int32_t n_sample, int32_t bc_x,
+                      int32_t bc_y, int32_t nearest, double x_period, double y_period, double epsl, const double* alp_dev,
+                      const double* x_nodes_dev, const double* y_nodes_dev, const double* t_arr_dev, const double* noise_dev,
+                      const double* x_init_dev, double* traj_x_dev, double* traj_alp_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

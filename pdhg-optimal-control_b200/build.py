@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", f) for f in ("pdhg_api.cu", "pdhg1d_cta.cu", "pdhg1d_k1.cu", "pdhg_aux.cu", "pdhg_coop.cu")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("pdhg_api.cu", "pdhg1d_cta.cu", "pdhg1d_k1.cu", "pdhg_aux.cu", "pdhg_traj.cu", "pdhg_coop.cu")]
 HDR = [os.path.join(HERE, "csrc", f) for f in ("pdhg_device.cuh", "pdhg_params.h")] + \
       [os.path.join(os.path.dirname(HERE), "include", "pdhg_b200.h")]
 OUT = os.path.join(HERE, "lib", "libpdhg_b200.so")

@@ -19,7 +19,7 @@ LOG_COLS = 4
 
 EXPORTS = ("pdhg_create", "pdhg_destroy", "pdhg_last_error", "pdhg_path", "pdhg_launch_count", "pdhg_last_kernel_ms", "pdhg_phase_times", "pdhg_debug_phase", "pdhg_ext_phase", "pdhg_update_primal",
            "pdhg_update_dual", "pdhg_solve_block", "pdhg_multi_step", "pdhg_multi_step_host", "pdhg_multi_step_range", "pdhg_get_march_state",
-           "pdhg_set_march_state")
+           "pdhg_set_march_state", "pdhg_compute_traj")
 
 
 class PdhgError(RuntimeError):
@@ -92,6 +92,8 @@ def load():
   lib.pdhg_get_march_state.argtypes = [vp, dp, dp, dp, vp]
   lib.pdhg_set_march_state.restype = C.c_int
   lib.pdhg_set_march_state.argtypes = [vp, dp, dp, dp, vp]
+  lib.pdhg_compute_traj.restype = C.c_int
+  lib.pdhg_compute_traj.argtypes = [i32] * 10 + [dbl, dbl, dbl] + [dp] * 8 + [vp]
   lib.pdhg_multi_step_host.restype = C.c_int
   lib.pdhg_multi_step_host.argtypes = [vp, dp, dp, dp, i64, i32, dp, dp, dp, C.POINTER(Logs)]
   _lib = lib
@@ -128,6 +130,16 @@ class LogBuffers:
     self.stepsz_final = np.zeros((B,), np.float64)
     self.inner_total = np.zeros((B,), np.int64)
     self.struct = Logs(*[_hptr(getattr(self, f[0])) for f in Logs._fields_])
+
+
+def compute_traj_dev(ndim, egno, n_ctrl, nx, ny, nt, n_sample, bc_x, bc_y, nearest, x_period, y_period, epsl, alp_ptr, xn_ptr, yn_ptr, t_ptr,
+                     noise_ptr, x0_ptr, traj_x_ptr, traj_alp_ptr, stream=None):
+  """pdhg_compute_traj on device pointers (ints from `tensor.data_ptr()`)."""
+  rc = load().pdhg_compute_traj(int(ndim), int(egno), int(n_ctrl), int(nx), int(ny), int(nt), int(n_sample), int(bc_x), int(bc_y), int(nearest),
+                                float(x_period), float(y_period), float(epsl), alp_ptr, xn_ptr, yn_ptr, t_ptr, noise_ptr, x0_ptr, traj_x_ptr,
+                                traj_alp_ptr, stream)
+  if rc != 0:
+    raise PdhgError(rc, "pdhg_compute_traj: bad argument or launch failure")
 
 
 class Solver:

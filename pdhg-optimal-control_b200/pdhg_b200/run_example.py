@@ -88,6 +88,72 @@ def solve_HJ_batch(ndim, n_ctrl, egno, epsl, fns_dict, nx, ny, nt, x_period, y_p
   return out
 
 
+def _traj_noise(epsl, shape, seed, noise):
+  """Standard normal increments [nt-1, n_sample(, 2)] in numpy.random's order (the reference draws them step by step from the
+  global stream, run_example.py:48,151); `seed` makes a run reproducible, `noise` injects the draws themselves."""
+  if epsl <= 0:
+    return None
+  if noise is not None:
+    return np.ascontiguousarray(np.asarray(noise, dtype=np.float64).reshape(shape))
+  rs = np.random.RandomState(seed) if seed is not None else np.random
+  return np.stack([rs.normal(size=shape[1:]) for _ in range(shape[0])])
+
+
+def compute_traj_1d(x_init, alp, fns_dict, nt, x_arr, t_arr, x_period, T, epsl=0.0, interp_method='linear', seed=None, noise=None):
+  """run_example.py:18-51 on the GPU (pdhg_compute_traj): alp [2, nt-1, nx], x_init [n_sample] ->
+  (traj_alp [nt-1, n_sample, 1], traj_x [nt, n_sample]).  `fns_dict` (instead of the reference's bare f_fn) names the dynamics."""
+  from . import _dev
+  t = _dev.require_cuda()
+  x_init = np.asarray(_np_(x_init), dtype=np.float64).ravel()
+  xa = np.asarray(_np_(x_arr), dtype=np.float64).ravel()
+  ns, nx = x_init.size, xa.size
+  alp_d = _dev.to_dev(alp)
+  if interp_method == 'nearest':
+    assert np.all(np.diff(xa) > 0), "nearest interpolation expects an ascending grid"      # (:38-39 compares with x_arr itself)
+  else:
+    xa = xa % x_period                                         # numpy.interp(period=): nodes reduced mod period and sorted
+    order = np.argsort(xa, kind="stable")
+    if not np.array_equal(order, np.arange(nx)):
+      xa = xa[order]
+      alp_d = alp_d[:, :, t.from_numpy(order).to(alp_d.device)].contiguous()
+  xa_dev = _dev.to_dev(xa)
+  nz = _traj_noise(epsl, (nt - 1, ns), seed, noise)
+  nz_d = _dev.to_dev(nz) if nz is not None else None
+  tx = t.empty((nt, ns), dtype=t.float64, device=alp_d.device)
+  ta = t.empty((nt - 1, ns, 1), dtype=t.float64, device=alp_d.device)
+  x0_d, t_d = _dev.to_dev(x_init), _dev.to_dev(np.asarray(_np_(t_arr), dtype=np.float64).ravel())
+  _lib.compute_traj_dev(1, fns_dict.egno, 1, nx, 1, nt, ns, 0, 0, interp_method == 'nearest', x_period, 1.0, epsl, alp_d.data_ptr(), xa_dev.data_ptr(),
+                        None, t_d.data_ptr(), nz_d.data_ptr() if nz_d is not None else None, x0_d.data_ptr(), tx.data_ptr(), ta.data_ptr(),
+                        _dev.stream_ptr())
+  return (ta, tx) if _dev.is_tensor(alp) else tuple(_dev.to_host([ta, tx]))
+
+
+def compute_traj_2d(x_init, alp, fns_dict, nt, x1_arr, x2_arr, t_arr, x_period, y_period, T, bc, center, epsl=0.0, interp_method='linear',
+                    seed=None, noise=None):
+  """run_example.py:113-155 on the GPU: alp [4, nt-1, nx, ny, n_ctrl], x_init [n_sample, 2] ->
+  (traj_alp [nt-1, n_sample, n_ctrl], traj_x [nt, n_sample, 2]).  bc (0, 0) periodic, (1, 0) edge-clamped in x (egno 3)."""
+  from . import _dev
+  t = _dev.require_cuda()
+  x_init = np.ascontiguousarray(np.asarray(_np_(x_init), dtype=np.float64).reshape(-1, 2))
+  ns = x_init.shape[0]
+  alp_d = _dev.to_dev(_np_(alp) if not _dev.is_tensor(alp) else alp)
+  nx, ny, n_ctrl = int(alp_d.shape[2]), int(alp_d.shape[3]), int(alp_d.shape[4])
+  nz = _traj_noise(epsl, (nt - 1, ns, 2), seed, noise)
+  nz_d = _dev.to_dev(nz) if nz is not None else None
+  tx = t.empty((nt, ns, 2), dtype=t.float64, device=alp_d.device)
+  ta = t.empty((nt - 1, ns, n_ctrl), dtype=t.float64, device=alp_d.device)
+  x1_d, x2_d = _dev.to_dev(np.asarray(_np_(x1_arr), dtype=np.float64).ravel()), _dev.to_dev(np.asarray(_np_(x2_arr), dtype=np.float64).ravel())
+  x0_d, t_d = _dev.to_dev(x_init), _dev.to_dev(np.asarray(_np_(t_arr), dtype=np.float64).ravel())
+  _lib.compute_traj_dev(2, fns_dict.egno, n_ctrl, nx, ny, nt, ns, bc[0], bc[1], interp_method == 'nearest', x_period, y_period, epsl, alp_d.data_ptr(),
+                        x1_d.data_ptr(), x2_d.data_ptr(), t_d.data_ptr(), nz_d.data_ptr() if nz_d is not None else None, x0_d.data_ptr(),
+                        tx.data_ptr(), ta.data_ptr(), _dev.stream_ptr())
+  return (ta, tx) if _dev.is_tensor(alp) else tuple(_dev.to_host([ta, tx]))
+
+
+def _np_(x):
+  return x.detach().cpu().numpy() if hasattr(x, "detach") else x
+
+
 def main(argv):
   from absl import flags
   FLAGS = flags.FLAGS
@@ -123,8 +189,30 @@ def main(argv):
                                  C=FLAGS.C, pow=FLAGS.pow, Ct=FLAGS.Ct, load_middle_dir=lmd, load_middle_prefix=lmp)
     if FLAGS.save:
       save(save_dir, filename_prefix, (results, errs_all))
-  if FLAGS.plot or FLAGS.tfboard or FLAGS.plot_traj_num_1d:
-    print('plotting / tensorboard / trajectory post-processing are outside this package (SURVEY.md section 8)')
+  if FLAGS.plot_traj_num_1d > 0 and results[0][3] is not None:
+    # closed-loop trajectories (run_example.py:342-393); the figures themselves are out of scope, the arrays are saved
+    alp = np.asarray(_np_(results[0][3]))
+    alp_rev = alp[:, ::-1]                                       # :356 time direction of the control
+    t_arr = np.linspace(0.0, FLAGS.T, num=nt)
+    n1 = FLAGS.plot_traj_num_1d
+    method = 'nearest' if egno == 2 else 'linear'
+    if egno == 3:
+      ys = np.linspace(-FLAGS.y_period / 2 + 0.1, FLAGS.y_period / 2 - 0.1, num=n1)[:, None]
+      if FLAGS.epsl > 0:
+        ys = 0 * ys
+      xs = np.pad(ys, ((0, 0), (1, 0)), mode='constant', constant_values=0.5)
+      traj_alp, traj_x = compute_traj_2d(xs, alp_rev, fns_dict, nt, x_arr[0, :, 0, 0], x_arr[0, 0, :, 1], t_arr, FLAGS.x_period, FLAGS.y_period,
+                                         FLAGS.T, bc, (centered, centered), FLAGS.epsl)
+    elif ndim == 1:
+      traj_alp, traj_x = compute_traj_1d(np.linspace(0, FLAGS.x_period, num=n1), alp_rev[..., 0], fns_dict, nt, x_arr[0, :, 0], t_arr,
+                                         FLAGS.x_period, FLAGS.T, FLAGS.epsl, method)
+    else:
+      xm, ym = np.meshgrid(np.linspace(0, FLAGS.x_period, num=n1), np.linspace(0, FLAGS.y_period, num=n1), indexing='ij')
+      traj_alp, traj_x = compute_traj_2d(np.stack([xm.flatten(), ym.flatten()], axis=-1), alp_rev, fns_dict, nt, x_arr[0, :, 0, 0], x_arr[0, 0, :, 1],
+                                         t_arr, FLAGS.x_period, FLAGS.y_period, FLAGS.T, bc, (centered, centered), FLAGS.epsl, method)
+    save(save_dir, filename_prefix + '_traj', (traj_alp, traj_x))
+  if FLAGS.plot or FLAGS.tfboard:
+    print('plotting / tensorboard are outside this package (SURVEY.md section 8)')
   print('phi: ', results[0][1])
   print('end')
 
