@@ -116,12 +116,15 @@ int pdhg_phase_times(pdhg_handle* h, double* out16);
  *   phase 4 = E: outer differences of (rho_out, alp_out) against (rho_in, alp_in)
  * Rows outside [sum_lo, sum_hi) (ghost rows) do not contribute to the error sums.  Phases 3 and 4 store the grid totals of the
  * reduced quantities (dual sums in 0..15, the preceding phase C's primal sums in 16..18, a fused second sweep in 20..35) to
- * bufs->sums (device, room for 36 doubles). */
+ * bufs->sums (device, room for 20 + 16 (pass_mask - 1) doubles, 84 at most). */
 typedef struct pdhg_ext_buffers {
   double *phi_in, *phi_out, *phib, *rho_in, *alp_in, *rho_out, *alp_out;
   void* zt;
   double* sums;
 } pdhg_ext_buffers;
+/* largest `pass_mask` (dual sweeps fused into one pass) phase 3 accepts for this handle; the sums of sweep s >= 2 of a pass land in
+ * slots 20 + 16 (s - 2) .. of bufs->sums, which then needs room for 20 + 16 (pass_mask - 1) doubles */
+int pdhg_max_fuse(pdhg_handle* h);
 int pdhg_ext_phase(pdhg_handle* h, int phase, int pass_mask, double step, double epsl, const pdhg_ext_buffers* bufs,
                    int sum_lo, int sum_hi, int nyh_override, int ky_off, int nyh_tab, void* stream);
 

@@ -19,6 +19,7 @@ size_t pdhg1d_cta_smem_bytes(int nx, int K);
 cudaError_t launch_pdhg_coop(const MarchParams& p, int B, void* ws, cudaStream_t stream, long long* launches);
 size_t pdhg_coop_workspace_bytes(const MarchParams& p, int B);
 cudaError_t coop_phase_times(const MarchParams& p, void* ws, double* out6);
+int coop_max_fuse(const MarchParams& p);
 cudaError_t launch_ext_phase(const MarchParams& p, void* ws, int phase, int pass_mask, double step, const ExtPhaseDesc& ext,
                              cudaStream_t stream);
 cudaError_t launch_debug_phase(const MarchParams& p, void* ws, int phase, int pass_mask, double step, cudaStream_t stream);
@@ -181,6 +182,14 @@ extern "C" int pdhg_phase_times(pdhg_handle* h, double* out6 /* 16 doubles */) {
   if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
   CU(coop_phase_times(p, h->ws, out6));
   return PDHG_OK;
+}
+
+extern "C" int pdhg_max_fuse(pdhg_handle* h) {
+  if (!h || h->path != 2) return 1;
+  DeviceGuard guard(h->cfg.device);
+  MarchParams p;
+  fill_params(h, &p);
+  return coop_max_fuse(p);
 }
 
 extern "C" int pdhg_ext_phase(pdhg_handle* h, int phase, int pass_mask, double step, double epsl, const pdhg_ext_buffers* bufs,

@@ -1948,7 +1948,7 @@ static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   }
   // fused dual sweeps: two per pass on the HBM-bound grids; more (up to kFuseMax) while the per-thread accumulator slots of
   // sweeps 3.. (3 + 4 ndim sums each) fit the work area (next to two ring stages when the TMA pipeline runs)
-  g.d_fuse = !hbm_bound ? 1 : ((g.fast_y || g.fast_x) ? kFuseMax : 2);
+  g.d_fuse = !hbm_bound ? 1 : kFuseMax;
   if (kn.dfuse > 0) g.d_fuse = kn.dfuse;
   if (g.d_fuse > kFuseMax) g.d_fuse = kFuseMax;
   if (g.d_fuse < 1) g.d_fuse = 1;
@@ -2078,6 +2078,15 @@ cudaError_t launch_debug_phase(const MarchParams& p, void* ws, int phase, int pa
 cudaError_t launch_ext_phase(const MarchParams& p, void* ws, int phase, int pass_mask, double step, const ExtPhaseDesc& ext,
                              cudaStream_t stream) {
   return coop_launch(p, ws, 0, MODE_PHASE, nullptr, nullptr, step, 0.0, nullptr, nullptr, stream, phase, pass_mask, &ext);
+}
+
+// largest number of dual sweeps one pass may fuse for this problem (what MODE_PHASE / slab-mode callers may ask for)
+int coop_max_fuse(const MarchParams& p) {
+  int dev = 0, sms = 0, smem_cap = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  return coop_geom(p, sms, ((size_t)smem_cap - 4096) / kCtasPerSm - (kCtasPerSm > 1 ? 2048 : 0)).d_fuse;
 }
 
 cudaError_t coop_phase_times(const MarchParams& p, void* ws, double* out6) {

@@ -19,7 +19,7 @@ LOG_COLS = 4
 
 EXPORTS = ("pdhg_create", "pdhg_destroy", "pdhg_last_error", "pdhg_path", "pdhg_launch_count", "pdhg_last_kernel_ms", "pdhg_phase_times", "pdhg_debug_phase", "pdhg_ext_phase", "pdhg_update_primal",
            "pdhg_update_dual", "pdhg_solve_block", "pdhg_multi_step", "pdhg_multi_step_host", "pdhg_multi_step_range", "pdhg_get_march_state",
-           "pdhg_set_march_state", "pdhg_compute_traj")
+           "pdhg_set_march_state", "pdhg_compute_traj", "pdhg_max_fuse")
 
 
 class PdhgError(RuntimeError):
@@ -92,6 +92,8 @@ def load():
   lib.pdhg_get_march_state.argtypes = [vp, dp, dp, dp, vp]
   lib.pdhg_set_march_state.restype = C.c_int
   lib.pdhg_set_march_state.argtypes = [vp, dp, dp, dp, vp]
+  lib.pdhg_max_fuse.restype = C.c_int
+  lib.pdhg_max_fuse.argtypes = [vp]
   lib.pdhg_compute_traj.restype = C.c_int
   lib.pdhg_compute_traj.argtypes = [i32] * 10 + [dbl, dbl, dbl] + [dp] * 8 + [vp]
   lib.pdhg_multi_step_host.restype = C.c_int
@@ -196,6 +198,10 @@ class Solver:
     eb = ExtBuffers(*[bufs.get(f[0]) for f in ExtBuffers._fields_])
     _check(self.lib.pdhg_ext_phase(self._h, int(phase), int(pass_mask), float(step), float(epsl), C.byref(eb), int(sum_lo), int(sum_hi),
                                    int(nyh_override), int(ky_off), int(nyh_tab), stream))
+
+  @property
+  def max_fuse(self):
+    return int(self.lib.pdhg_max_fuse(self._h))
 
   def debug_phase(self, phase, pass_mask=7, step=0.05, reps=1):
     _check(self.lib.pdhg_debug_phase(self._h, int(phase), int(pass_mask), float(step), int(reps)))

@@ -16,8 +16,8 @@ import numpy as np
 from . import _dev, _lib
 from .set_fns import coef_tables
 
-NQ = 36      # totals a phase launch hands out: 0..15 dual sweep, 16..18 primal, 20..35 second sweep of a fused pair
-FUSE = 2     # dual sweeps per pass while the inner loop is long (as the single-GPU kernel does; 2 needs no extra buffers)
+NQ = 84      # totals a phase launch hands out: 0..15 dual sweep, 16..18 primal, 20 + 16 (s - 2) ..: sweep s >= 2 of a fused pass
+FUSE = 5     # dual sweeps per pass while the inner loop is long, capped by what the handle can fuse (pdhg_max_fuse)
 
 
 class SlabRank:
@@ -56,6 +56,8 @@ class SlabRank:
     self.ztB = t.zeros((1, max(self.kyl, 1), nx), dtype=c128, device=self.dev)
     self.sums = z(NQ)
     self.cp, self.cd = 0, 0
+    self.fuse = max(1, min(FUSE, self.hL.max_fuse))
+    self._stream = _dev.stream_ptr(self.dev.index)
 
   def interior(self, a):
     return a[..., 1:self.nxl + 1, :]
@@ -64,7 +66,7 @@ class SlabRank:
     scalars = ("nyh_override", "ky_off", "nyh_tab", "pass_mask")
     ptr = {k: (v.data_ptr() if v is not None else None) for k, v in kw.items() if k not in scalars}
     extra = {k: v for k, v in kw.items() if k in scalars}
-    h.ext_phase(phase, step, epsl, 1, self.nxl + 1, stream=_dev.stream_ptr(self.dev.index), **extra, **ptr)
+    h.ext_phase(phase, step, epsl, 1, self.nxl + 1, stream=self._stream, **extra, **ptr)
 
 
 class LocalGroup:
@@ -121,29 +123,34 @@ class DistGroup:
     self.P = dist.get_world_size()
 
   def halo(self, get):
+    """Ghost rows of every array `get(R)` returns, ONE message per neighbour: the boundary rows of all arrays are packed into
+    one send buffer per direction (a grouped send/recv of 2 messages instead of 2 per array)."""
     t = _dev.torch()
     dist, R = self.dist, self.ranks[0]
     P, r = self.P, R.rank
-    left, right = (r - 1) % P, (r + 1) % P
-    ops, pend = [], []
-    for a in get(R):
-      s_first, s_last = a[..., 1, :].contiguous(), a[..., R.nxl, :].contiguous()
-      g_left, g_right = t.empty_like(s_first), t.empty_like(s_first)
-      # (order matters when left == right, P = 2: NCCL matches the sends and receives of a peer pair in issue order, and the
-      #  left ghost has to receive the neighbour's LAST interior row)
-      ops += [dist.P2POp(dist.isend, s_last, right), dist.P2POp(dist.isend, s_first, left),
-              dist.P2POp(dist.irecv, g_left, left), dist.P2POp(dist.irecv, g_right, right)]
-      pend.append((a, g_left, g_right))
+    arrs = list(get(R))
     if P == 1:
-      for a, _, _ in pend:
+      for a in arrs:
         a[..., 0, :] = a[..., R.nxl, :]
         a[..., R.nxl + 1, :] = a[..., 1, :]
       return
+    left, right = (r - 1) % P, (r + 1) % P
+    firsts = [a[..., 1, :].reshape(-1) for a in arrs]
+    lasts = [a[..., R.nxl, :].reshape(-1) for a in arrs]
+    s_first, s_last = t.cat(firsts), t.cat(lasts)
+    g_left, g_right = t.empty_like(s_last), t.empty_like(s_first)
+    # (order matters when left == right, P = 2: NCCL matches the sends and receives of a peer pair in issue order, and the
+    #  left ghost has to receive the neighbour's LAST interior row)
+    ops = [dist.P2POp(dist.isend, s_last, right), dist.P2POp(dist.isend, s_first, left),
+           dist.P2POp(dist.irecv, g_left, left), dist.P2POp(dist.irecv, g_right, right)]
     for w in dist.batch_isend_irecv(ops):
       w.wait()
-    for a, g_left, g_right in pend:
-      a[..., 0, :] = g_left
-      a[..., R.nxl + 1, :] = g_right
+    off = 0
+    for a, f in zip(arrs, firsts):
+      n = f.numel()
+      a[..., 0, :] = g_left[off:off + n].view(a[..., 0, :].shape)
+      a[..., R.nxl + 1, :] = g_right[off:off + n].view(a[..., 0, :].shape)
+      off += n
 
   def _a2a(self, send):
     t = _dev.torch()
@@ -235,7 +242,7 @@ def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_ite
 
     while j < rho_alp_iters:
       src, dst = last, (f2 if last == f1 else f1)
-      ns = max(1, min(prev_j - j, rho_alp_iters - j, FUSE))
+      ns = max(1, min(prev_j - j, rho_alp_iters - j, ranks[0].fuse))
       for R in ranks:
         R.ext(R.hL, 3, sigma, epsl, pass_mask=ns, phib=R.phib, rho_in=R.rho[src], alp_in=R.alp[src], rho_out=R.rho[dst], alp_out=R.alp[dst],
               sums=R.sums)
