@@ -1901,7 +1901,7 @@ struct ArgsSlot { cudaEvent_t ev = nullptr; cudaStream_t stream = nullptr; bool 
 static ArgsSlot g_args_slot[kMaxDevices];
 static std::mutex g_args_mutex;
 
-struct CoopGeom { int nxe, nye, nyh, TR, TKY, grid, d_fuse, fast_y, fast_x, tma_d, tma_R, tma_S, work_bytes; size_t smem; };
+struct CoopGeom { int nxe, nye, nyh, TR, TKY, grid, d_fuse, d_fuse_ext, fast_y, fast_x, tma_d, tma_R, tma_S, work_bytes; size_t smem; };
 
 static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   CoopGeom g;
@@ -1960,6 +1960,11 @@ static CoopGeom coop_geom(const MarchParams& p, int sm_count, size_t smem_cap) {
   } else {
     while (g.d_fuse > 2 && xacc_bytes(g.d_fuse) > (work > cap ? cap : work)) --g.d_fuse;
   }
+  // slab mode (MODE_PHASE, host-driven passes): fusing saves a launch and an all-reduce per sweep whatever the grid size, so the
+  // cap only depends on what the work area holds
+  g.d_fuse_ext = kFuseMax;
+  if (kn.dfuse > 0 && kn.dfuse < g.d_fuse_ext) g.d_fuse_ext = kn.dfuse;
+  while (g.d_fuse_ext > 2 && xacc_bytes(g.d_fuse_ext) + (g.tma_d ? 2 * stage : 0) > (work > cap ? cap : work)) --g.d_fuse_ext;
   g.work_bytes = (int)work;
   g.smem = tab + work;
   g.grid = sm_count * kCtasPerSm;
@@ -2037,6 +2042,7 @@ static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, 
   }
   a.dbg_phase = dbg_phase; a.dbg_pass = dbg_pass;
   a.sum_lo = 0; a.sum_hi = g.nxe; a.ky_off = 0; a.nyh_tab = g.nyh;
+  if (mode == MODE_PHASE) a.d_fuse = g.d_fuse_ext;
   if (ext) apply_ext(*ext, a);
   a.op_phi_in = op_in; a.op_phi_out = op_out; a.op_step = op_step; a.op_eps = op_eps; a.op_ninner = op_ninner; a.op_err = op_err;
   a.r_idt = 1.0 / p.dt; a.r_idx = 1.0 / a.dxe; a.r_idy = 1.0 / a.dye; a.r_idx2 = 1.0 / (a.dxe * a.dxe); a.r_idy2 = 1.0 / (a.dye * a.dye);
@@ -2086,7 +2092,7 @@ int coop_max_fuse(const MarchParams& p) {
   if (cudaGetDevice(&dev) != cudaSuccess) return 1;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  return coop_geom(p, sms, ((size_t)smem_cap - 4096) / kCtasPerSm - (kCtasPerSm > 1 ? 2048 : 0)).d_fuse;
+  return coop_geom(p, sms, ((size_t)smem_cap - 4096) / kCtasPerSm - (kCtasPerSm > 1 ? 2048 : 0)).d_fuse_ext;
 }
 
 cudaError_t coop_phase_times(const MarchParams& p, void* ws, double* out6) {

@@ -11,6 +11,9 @@ batched point-to-point sends for the halo rows.  `LocalGroup` runs the same algo
 process on one GPU (tensor copies instead of collectives) — that is how the decomposition is parity-tested without a
 multi-GPU box.  Restrictions of this first version: 2-D, periodic, time_step_per_PDHG = 2 (K = 1), nx divisible by P.
 """
+import os
+import time
+
 import numpy as np
 
 from . import _dev, _lib
@@ -56,7 +59,7 @@ class SlabRank:
     self.ztB = t.zeros((1, max(self.kyl, 1), nx), dtype=c128, device=self.dev)
     self.sums = z(NQ)
     self.cp, self.cd = 0, 0
-    self.fuse = max(1, min(FUSE, self.hL.max_fuse))
+    self.fuse = max(1, min(int(os.environ.get("PDHG_SLAB_FUSE", FUSE)), self.hL.max_fuse))
     self._stream = _dev.stream_ptr(self.dev.index)
 
   def interior(self, a):
@@ -199,9 +202,22 @@ def init_block(group, g_global, c_on_rho):
   group.halo(lambda R: R.phi + [R.phib])
 
 
+PROFILE = {}     # PDHG_SLAB_PROF=1: seconds per section of solve_block_slab (synchronising timers; diagnostic only)
+
+
+def _tick(name, t0):
+  if t0 is None:
+    return None
+  _dev.torch().cuda.synchronize()
+  now = time.perf_counter()
+  PROFILE[name] = PROFILE.get(name, 0.0) + now - t0
+  return now
+
+
 def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_iters=10):
   """PDHG_solver_oneiter (utils_pdhg_solver.py:9-94) on the slab-decomposed block.  Returns (iters, end_reason, err1, err2, n_inner)."""
   t = _dev.torch()
+  prof = os.environ.get("PDHG_SLAB_PROF") is not None
   tau, sigma = stepsz_param / 1.5, stepsz_param * 1.5
   ranks = group.ranks
   # norms of the starting iterate (interior rows), all-reduced
@@ -217,18 +233,29 @@ def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_ite
   prev_j = rho_alp_iters
   it = 0
   for it in range(n_maxiter):
+    tk = None
+    if prof:
+      t.cuda.synchronize()
+      tk = time.perf_counter()
     group.halo(lambda R: [R.rho[R.cd], R.alp[R.cd][0], R.alp[R.cd][1]])
+    tk = _tick("halo1", tk)
     for R in ranks:
       R.ext(R.hL, 0, 0.0, epsl, rho_in=R.rho[R.cd], alp_in=R.alp[R.cd], zt=R.zt)
+    tk = _tick("A", tk)
     group.transpose_fwd()
+    tk = _tick("a2a_fwd", tk)
     for R in ranks:
       if R.kyn > 0:
         R.ext(R.hB, 1, 0.0, epsl, zt=R.ztB, nyh_override=R.kyn, ky_off=R.ky0, nyh_tab=R.nyh)
+    tk = _tick("B", tk)
     group.transpose_bwd()
+    tk = _tick("a2a_bwd", tk)
     for R in ranks:
       # phase C of the local handle normalises the inverse transforms by 1 / (nxp ny); the x-transform ran over the global nx
       R.ext(R.hL, 2, tau * R.nxp / R.nx, epsl, zt=R.zt, phi_in=R.phi[R.cp], phi_out=R.phi[R.cp ^ 1], phib=R.phib)
+    tk = _tick("C", tk)
     group.halo(lambda R: [R.phib])
+    tk = _tick("halo2", tk)
     # inner dual loop, as in the single-GPU kernel: buffer cd stays intact, the passes ping-pong between the other two; while
     # the previous outer iteration needed several sweeps two sweeps are fused per pass (one launch, one all-reduce), and an
     # exit after the first sweep of a pair is handled by redoing exactly that sweep from the pair's input
@@ -246,7 +273,9 @@ def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_ite
       for R in ranks:
         R.ext(R.hL, 3, sigma, epsl, pass_mask=ns, phib=R.phib, rho_in=R.rho[src], alp_in=R.alp[src], rho_out=R.rho[dst], alp_out=R.alp[dst],
               sums=R.sums)
+      tk = _tick("D_pass", tk)
       v = group.allreduce_sums()
+      tk = _tick("allreduce", tk)
       if j == 0:
         e1s0, e1s1, e1nan = v[16], v[17], v[18]
       hit = -1
