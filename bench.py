@@ -382,8 +382,7 @@ def slab_line(rank, world, local, dist, nx=2048, iters=30):
   with contextlib.redirect_stdout(io.StringIO()):
     fns = sf.set_up_example_fns(1, 2, 0)
   g = sf.set_up_J(1, 2, (2.0, 2.0))(x_arr)[0]
-  R = slab.SlabRank(rank, world, fns, nx, ny, T, (2.0 / nx, 2.0 / ny), 70.0, x_arr, device=local)
-  grp = slab.DistGroup(R, dist)
+  R, grp, kind = slab.make_dist_rank(rank, world, dist, fns, nx, ny, T, (2.0 / nx, 2.0 / ny), 70.0, x_arr, device=local)
   out = {}
   for label, n in (("warm", 3), ("timed", iters)):
     slab.init_block(grp, g, 70.0)
@@ -396,7 +395,8 @@ def slab_line(rank, world, local, dist, nx=2048, iters=30):
   dist.all_reduce(t, op=dist.ReduceOp.MAX)
   it_s, n_in = out["timed"][1][0], out["timed"][1][4]
   return {"workload": "BASELINE configs[4] grid: egno=1 ndim=2 epsl=0.1 nx=ny=%d tsp=2 stepsz_param=5e-4, block 0, x-slab decomposed over %d GPUs "
-                      "(NCCL: 2 halo exchanges, 2 all-to-all transposes, 1 all-reduce per dual pass and iteration)" % (nx, world),
+                      "(2 halo exchanges, 2 transposes of the half spectrum, 1 sum all-reduce per dual pass and iteration)" % (nx, world),
+          "exchange": {"symm": "NVLink peer-memory stores + device-side barrier (torch symmetric memory)", "nccl": "NCCL collectives"}[kind],
           "iters": it_s, "inner_sweeps_per_iter": n_in / max(it_s, 1), "seconds": float(t[0]), "pdhg_iters_per_s": it_s / float(t[0]),
           "grid_point_updates_per_s": it_s * nx * ny / float(t[0]), "ms_per_iter": float(t[0]) / max(it_s, 1) * 1e3}
 

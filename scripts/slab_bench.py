@@ -36,8 +36,7 @@ def main():
   with contextlib.redirect_stdout(io.StringIO()):
     fns = sf.set_up_example_fns(1, 2, 0)
   g = sf.set_up_J(1, 2, (2.0, 2.0))(x_arr)[0]
-  R = slab.SlabRank(rank, world, fns, nx, ny, T, (2.0 / nx, 2.0 / ny), 70.0, x_arr, device=local)
-  grp = slab.DistGroup(R, dist)
+  R, grp, kind = slab.make_dist_rank(rank, world, dist, fns, nx, ny, T, (2.0 / nx, 2.0 / ny), 70.0, x_arr, device=local)
   out = {}
   for label, n in (("warm", 3), ("timed", iters)):
     slab.init_block(grp, g, 70.0)
@@ -71,7 +70,9 @@ def main():
             "slab_seconds": float(t_slab[0]), "slab_iters_per_s": it_s / float(t_slab[0]),
             "single_gpu_seconds_incl_h2d_d2h": t1, "single_gpu_iters_per_s": it_1 / t1,
             "parity_rel_linf_rank0_slab_vs_single_gpu": par,
-            "collectives_per_iteration": "2 halo exchanges (batch_isend_irecv), 2 all_to_all_single, 1 all_reduce per dual sweep",
+            "exchange": kind,
+            "exchanges_per_iteration": "2 halo exchanges, 2 transposes of the half spectrum, 1 sum all-reduce per dual pass (symm: peer stores + "
+                                       "device barrier over NVLink; nccl: batch_isend_irecv / all_to_all_single / all_reduce)",
             "note": "host-driven phases (one launch per phase, exit tests on the host after each all-reduce)"}
     print(json.dumps(line), flush=True)
   dist.barrier()

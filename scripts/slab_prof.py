@@ -15,8 +15,7 @@ with contextlib.redirect_stdout(io.StringIO()):
 g = sf.set_up_J(1, 2, (2.0, 2.0))(x_arr)[0]
 for fuse in (2, 5):
   os.environ["PDHG_SLAB_FUSE"] = str(fuse)
-  R = slab.SlabRank(rank, world, fns, nx, nx, 1.0 / 256, (2.0 / nx, 2.0 / nx), 70.0, x_arr, device=local)
-  grp = slab.DistGroup(R, dist)
+  R, grp, kind = slab.make_dist_rank(rank, world, dist, fns, nx, nx, 1.0 / 256, (2.0 / nx, 2.0 / nx), 70.0, x_arr, device=local)
   for prof in (False, True):
     if prof: os.environ["PDHG_SLAB_PROF"] = "1"
     else: os.environ.pop("PDHG_SLAB_PROF", None)
@@ -28,6 +27,6 @@ for fuse in (2, 5):
     res = slab.solve_block_slab(grp, 0.1, 5e-4, iters)
     torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
     if rank == 0:
-      print(json.dumps({"P": world, "fuse_asked": fuse, "fuse": R.fuse, "prof": prof, "ms_per_iter": dt / iters * 1e3, "n_inner": res[4],
+      print(json.dumps({"P": world, "exchange": kind, "fuse_asked": fuse, "fuse": R.fuse, "prof": prof, "ms_per_iter": dt / iters * 1e3, "n_inner": res[4],
                         "sections_ms_per_iter": {k: round(v / iters * 1e3, 3) for k, v in slab.PROFILE.items()}}), flush=True)
 dist.destroy_process_group()

@@ -69,15 +69,50 @@ def test_dist_group_world1_equals_local_group(built_lib):
   if created:
     dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
   try:
-    for kind in ("local", "dist"):
-      R = slab.SlabRank(0, 1, fns, nx, ny, T, (2.0 / nx, 2.0 / ny), 70.0, x_arr)
-      grp = slab.LocalGroup([R]) if kind == "local" else slab.DistGroup(R, dist)
+    for kind in ("local", "dist", "symm"):
+      if kind == "symm":
+        # NVLink peer-memory flavour (torch symmetric memory): at world size 1 every "peer" store lands in the rank's own arena
+        try:
+          R, grp, _ = slab.make_dist_rank(0, 1, dist, fns, nx, ny, T, (2.0 / nx, 2.0 / ny), 70.0, x_arr, kind="symm")
+        except Exception as ex:      # symmetric memory needs CUDA VMM support of the driver/box
+          print("symmetric memory unavailable here:", repr(ex))
+          continue
+      else:
+        R = slab.SlabRank(0, 1, fns, nx, ny, T, (2.0 / nx, 2.0 / ny), 70.0, x_arr)
+        grp = slab.LocalGroup([R]) if kind == "local" else slab.DistGroup(R, dist)
       slab.init_block(grp, g, 70.0)
       it = slab.solve_block_slab(grp, 0.0, 0.1, 30)
       out.append((it, slab.gather_block(grp)))
   finally:
     if created:
       dist.destroy_process_group()
-  assert out[0][0][:2] == out[1][0][:2]
-  for a, b in zip(out[0][1], out[1][1]):
+  for o in out[1:]:
+    assert out[0][0][:2] == o[0][:2]
+    for a, b in zip(out[0][1], o[1]):
+      assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("P,nx,ny,epsl,nmax,stepsz", [(2, 32, 24, 0.0, 5000, 0.1), (3, 48, 16, 0.1, 400, 0.05)])
+def test_speculative_pass_plan_equals_pass_by_pass_bitwise(built_lib, monkeypatch, P, nx, ny, epsl, nmax, stepsz):
+  """solve_block_slab enqueues all dual passes the previous iteration's sweep count predicts and exchanges their sums once
+  (PDHG_SLAB_SPEC, default on); a wrong prediction is redone pass by pass.  Same iterates, same stopping iteration, bit for bit,
+  as the pass-by-pass loop - on runs whose sweep count changes along the way (so that both outcomes of the prediction occur)."""
+  from pdhg_b200 import run_example as rx, set_fns as sf, slab
+  from pdhg_b200.set_fns import set_up_J
+  T = 0.05
+  x_arr = rx.make_x_arr(2, nx, ny, 2.0, 2.0)
+  fns, _ = quiet(sf.set_up_example_fns, 1, 2, 0)
+  g = set_up_J(1, 2, (2.0, 2.0))(x_arr)[0]
+  out = {}
+  for spec in ("0", "1"):
+    monkeypatch.setenv("PDHG_SLAB_SPEC", spec)
+    ranks = [slab.SlabRank(r, P, fns, nx, ny, T, (2.0 / nx, 2.0 / ny), 70.0, x_arr) for r in range(P)]
+    grp = slab.LocalGroup(ranks)
+    slab.init_block(grp, g, 70.0)
+    res = slab.solve_block_slab(grp, epsl, stepsz, nmax)
+    out[spec] = (res, slab.gather_block(grp), dict(slab.STATS))
+  assert out["0"][0] == out["1"][0], (out["0"][0], out["1"][0])
+  for a, b in zip(out["0"][1], out["1"][1]):
     assert np.array_equal(a, b)
+  assert out["0"][2]["respeculated"] == 0
+  print("iterations", out["1"][2]["iters"], "of which redone pass by pass", out["1"][2]["respeculated"], "inner sweeps", out["1"][0][4])
