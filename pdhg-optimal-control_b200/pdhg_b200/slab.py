@@ -100,7 +100,7 @@ class LocalGroup:
     self.ranks = ranks
     self.P = len(ranks)
 
-  def halo(self, get):
+  def halo(self, get, fenced=False):
     P = self.P
     for r, R in enumerate(self.ranks):
       for a, left, right in zip(get(R), get(self.ranks[(r - 1) % P]), get(self.ranks[(r + 1) % P])):
@@ -136,10 +136,16 @@ class LocalGroup:
   def sync(self):
     pass
 
+  def sums_begin(self, n=None):
+    """Totals over the ranks of the first n rows of every rank's `sums` (all of it if n is None): enqueue ..."""
+    return sum((R.sums if n is None else R.sums[:n]).clone() for R in self.ranks)
+
+  def sums_end(self, tok):
+    """... and read them on the host."""
+    return tok.cpu().numpy()
+
   def allreduce_sums(self, n=None):
-    """Totals over the ranks of the first n rows of every rank's `sums` (all of it if n is None), on the host."""
-    tot = sum((R.sums if n is None else R.sums[:n]).clone() for R in self.ranks)
-    return tot.cpu().numpy()
+    return self.sums_end(self.sums_begin(n))
 
 
 class DistGroup:
@@ -150,7 +156,7 @@ class DistGroup:
     self.dist = dist
     self.P = dist.get_world_size()
 
-  def halo(self, get):
+  def halo(self, get, fenced=False):
     """Ghost rows of every array `get(R)` returns, ONE message per neighbour: the boundary rows of all arrays are packed into
     one send buffer per direction (a grouped send/recv of 2 messages instead of 2 per array)."""
     t = _dev.torch()
@@ -213,17 +219,23 @@ class DistGroup:
   def sync(self):
     pass
 
-  def allreduce_sums(self, n=None):
+  def sums_begin(self, n=None):
     R = self.ranks[0]
     x = R.sums if n is None else R.sums[:n]
     self.dist.all_reduce(x)
-    return x.cpu().numpy()
+    return x
+
+  def sums_end(self, tok):
+    return tok.cpu().numpy()
+
+  def allreduce_sums(self, n=None):
+    return self.sums_end(self.sums_begin(n))
 
 
 class SymmGroup(DistGroup):
   """One rank per process, exchanges over NVLink PEER MEMORY instead of NCCL calls: every exchanged buffer lives in a symmetric-memory
   arena (torch.distributed._symmetric_memory: CUDA VMM allocations mapped into every rank of the node), so
-    * a halo exchange   = two strided copy kernels that STORE this rank's boundary rows straight into the neighbours' ghost rows,
+    * a halo exchange   = two strided copy kernels that LOAD the neighbours' boundary rows straight into this rank's ghost rows,
     * an FFT transpose  = P strided copies of this rank's [ky-range of d] x [own x-rows] block straight into rank d's ky-slab (no pack,
                           no permute / contiguous staging, no unpack),
     * the sum all-reduce = P stores of this rank's 84 totals into slot [rank] of every peer + one local sum in fixed rank order (every
@@ -240,6 +252,9 @@ class SymmGroup(DistGroup):
     self.peer_arena = [self.hdl.get_buffer(r, (n,), t.float64) for r in range(self.P)]
     self.base = rank_state.arena.storage_offset()
     self.set = 0
+    self._cache = {}
+    self.side = t.cuda.Stream(device=rank_state.dev)
+    self.ev_main, self.ev_side = t.cuda.Event(), t.cuda.Event()
 
   @staticmethod
   def allocator(device):
@@ -253,51 +268,112 @@ class SymmGroup(DistGroup):
     p = self.peer_arena[r]
     return t.as_strided(p, a.shape, a.stride(), p.storage_offset() + a.storage_offset() - self.base)
 
-  def halo(self, get):
+  def _pairs(self, key, build):
+    """(destination view in a peer's arena, source view) pairs of one exchange, built once: slicing and as_strided cost the host
+    several microseconds per view, and an iteration has ~10 of these copies on its critical path."""
+    p = self._cache.get(key)
+    if p is None:
+      p = self._cache[key] = build()
+    return p
+
+  def halo(self, get, fenced=False):
+    """PULL model: after a barrier (skipped if the caller says one already separates the neighbours' producing kernels from this
+    call: `fenced`), this rank loads the neighbours' boundary rows into its own ghost rows.  (A push would race: the kernels that
+    produce an array also write its ghost rows - with values that mean nothing - so a neighbour's early store could be overwritten
+    by this rank's own late kernel.  The sources of a pull are interior rows, which only their owner writes, many barriers later.)"""
     R, P = self.ranks[0], self.P
-    left, right = (R.rank - 1) % P, (R.rank + 1) % P
-    for a in get(R):
-      self._peer(a[..., 0, :], right).copy_(a[..., R.nxl, :])          # my last interior row -> right neighbour's lower ghost row
-      self._peer(a[..., R.nxl + 1, :], left).copy_(a[..., 1, :])        # my first interior row -> left neighbour's upper ghost row
-    self.hdl.barrier()
+    arrs = get(R)
+
+    def build():
+      left, right = (R.rank - 1) % P, (R.rank + 1) % P
+      out = []
+      for a in arrs:
+        out.append((a[..., 0, :], self._peer(a[..., R.nxl, :], left)))            # lower ghost row <- left neighbour's last interior row
+        out.append((a[..., R.nxl + 1, :], self._peer(a[..., 1, :], right)))       # upper ghost row <- right neighbour's first interior row
+      return out
+
+    if not fenced:
+      self.hdl.barrier()
+    for dst, src in self._pairs(("halo",) + tuple(a.data_ptr() for a in arrs), build):
+      dst.copy_(src)
 
   def transpose_fwd(self):
-    t = _dev.torch()
     R, P = self.ranks[0], self.P
-    K, kyl, nxl, nyh = R.K, R.kyl, R.nxl, R.nyh
-    zr, zb = t.view_as_real(R.zt), t.view_as_real(R.ztB)                # [K][nyh][nxp][2], [K][kyl][nx][2]
-    for d in range(P):
-      k0 = min(d * kyl, nyh)
-      kn = max(0, min(kyl, nyh - k0))
-      if kn > 0:
-        self._peer(zb[:, :kn, R.rank * nxl:(R.rank + 1) * nxl, :], d).copy_(zr[:, k0:k0 + kn, 1:nxl + 1, :])
+
+    def build():
+      t = _dev.torch()
+      kyl, nxl, nyh = R.kyl, R.nxl, R.nyh
+      zr, zb = t.view_as_real(R.zt), t.view_as_real(R.ztB)                # [K][nyh][nxp][2], [K][kyl][nx][2]
+      out = []
+      for d in range(P):
+        k0 = min(d * kyl, nyh)
+        kn = max(0, min(kyl, nyh - k0))
+        if kn > 0:
+          out.append((self._peer(zb[:, :kn, R.rank * nxl:(R.rank + 1) * nxl, :], d), zr[:, k0:k0 + kn, 1:nxl + 1, :]))
+      return out
+
+    for dst, src in self._pairs("fwd", build):
+      dst.copy_(src)
     self.hdl.barrier()
 
   def transpose_bwd(self):
-    t = _dev.torch()
     R, P = self.ranks[0], self.P
-    nxl = R.nxl
-    zr, zb = t.view_as_real(R.zt), t.view_as_real(R.ztB)
-    if R.kyn > 0:
-      for d in range(P):
-        self._peer(zr[:, R.ky0:R.ky0 + R.kyn, 1:nxl + 1, :], d).copy_(zb[:, :R.kyn, d * nxl:(d + 1) * nxl, :])
+
+    def build():
+      t = _dev.torch()
+      nxl = R.nxl
+      zr, zb = t.view_as_real(R.zt), t.view_as_real(R.ztB)
+      if R.kyn <= 0:
+        return []
+      return [(self._peer(zr[:, R.ky0:R.ky0 + R.kyn, 1:nxl + 1, :], d), zb[:, :R.kyn, d * nxl:(d + 1) * nxl, :]) for d in range(P)]
+
+    for dst, src in self._pairs("bwd", build):
+      dst.copy_(src)
     self.hdl.barrier()
 
   def sync(self):
     """All ranks' earlier work on their streams is complete before any rank's later work starts (device-side, no host wait)."""
     self.hdl.barrier()
 
-  def allreduce_sums(self, n=None):
+  def sums_begin(self, n=None):
+    """Stores this rank's rows into slot [rank] of every peer, barrier, then copies all P slots to pinned host memory on a SIDE
+    stream: the host can wait for exactly that copy (sums_end) while later work is already queued on the main stream."""
+    t = _dev.torch()
     R, P = self.ranks[0], self.P
     x = R.sums if n is None else R.sums[:n]
     m = x.numel()
     s = self.set
     self.set ^= 1                                   # two alternating sets: a fast rank's next pass never overwrites what a slow one still sums
-    mine = R.sums_all[s, R.rank, :m]
-    for r in range(P):
-      self._peer(mine, r).copy_(x.reshape(-1))
+
+    def build():
+      mine = R.sums_all[s, R.rank, :m]
+      stage = t.empty((P, m), dtype=t.float64, device=R.dev)
+      host = t.empty((P, m), dtype=t.float64, pin_memory=True)
+      return [(self._peer(mine, r), x.reshape(-1)) for r in range(P)] + [(stage, R.sums_all[s, :, :m]), (host, stage)]
+
+    pairs = self._pairs(("sums", s, m), build)
+    for dst, src in pairs[:-2]:
+      dst.copy_(src)
     self.hdl.barrier()
-    return R.sums_all[s, :, :m].sum(dim=0).view(x.shape).cpu().numpy()
+    pairs[-2][0].copy_(pairs[-2][1])
+    self.ev_main.record()
+    with t.cuda.stream(self.side):
+      self.side.wait_event(self.ev_main)
+      pairs[-1][0].copy_(pairs[-1][1], non_blocking=True)
+      self.ev_side.record(self.side)
+    return pairs[-1][0], tuple(x.shape)
+
+  def sums_end(self, tok):
+    host, shape = tok
+    self.ev_side.synchronize()
+    rows = host.numpy()                             # [P][m]: every rank adds the same rows in the same (rank) order
+    tot = rows[0].copy()
+    for r in range(1, self.P):
+      tot += rows[r]
+    return tot.reshape(shape)
+
+  def allreduce_sums(self, n=None):
+    return self.sums_end(self.sums_begin(n))
 
 
 def make_dist_rank(rank, world, dist, *args, kind=None, **kw):
@@ -324,8 +400,8 @@ def init_block(group, g_global, c_on_rho):
     for b in R.alp:
       b.zero_()
     R.cp, R.cd = 0, 0
-  group.sync()              # peer-memory halos store into the neighbours' ghost rows: not before the neighbour has filled its buffers
   group.halo(lambda R: R.phi + [R.phib])
+  group.sync()
 
 
 STATS = {}       # of the last solve_block_slab call: outer iterations and how many of them had to redo their dual loop pass by pass
@@ -355,21 +431,27 @@ def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_ite
                 [(it_(R.alp[R.cd][q]) ** 2).sum() for q in range(4)])
     loc.append(v)
   tot = group.allreduce(loc)[0].cpu().numpy()
+  group.sync()
   S_row0, S_rho, S_alp = tot[0], tot[1], tot[2:6].copy()
   n_inner, reason, err1, err2 = 0, _lib.END_MAXITER, float("nan"), float("nan")
   prev_j = rho_alp_iters
   spec = os.environ.get("PDHG_SLAB_SPEC", "1") != "0"
   n_respec = 0
-  it = 0
-  for it in range(n_maxiter):
-    tk = None
-    if prof:
-      t.cuda.synchronize()
-      tk = time.perf_counter()
-    group.halo(lambda R: [R.dual[R.cd][0:3]])              # rho, alp1_x, alp2_x
+  trace = os.environ.get("PDHG_SLAB_TRACE") is not None and ranks[0].rank == 0
+  ahead = spec and not prof and os.environ.get("PDHG_SLAB_AHEAD", "1") != "0"
+  front_for = None          # dual buffer for which the first half of the next iteration is already in the stream
+  _NUM = np.array([[b0 + 2 * q for q in range(5)] for b0 in [0] + [20 + 16 * sw for sw in range((NQ - 20) // 16)]])      # [sweep of a pass][rho, alp 1..4]
+  _DEN = _NUM + 1
+
+  def front(b, tk=None):
+    """First half of an outer iteration on dual buffer b: ghost rows of (rho, alp1_x, alp2_x), continuity residual + y-transform,
+    transpose, x-transform / time solve on this rank's ky-slab, transpose back.  Writes only zt, ztB and ghost rows."""
+    # (the barrier of the preceding sum exchange - or the one at the start of the solve - already orders the neighbours' dual
+    #  sweeps before this point)
+    group.halo(lambda R: [R.dual[b][0:3]], fenced=True)
     tk = _tick("halo1", tk)
     for R in ranks:
-      R.ext(R.hL, 0, 0.0, epsl, rho_in=R.rho[R.cd], alp_in=R.alp[R.cd], zt=R.zt)
+      R.ext(R.hL, 0, 0.0, epsl, rho_in=R.rho[b], alp_in=R.alp[b], zt=R.zt)
     tk = _tick("A", tk)
     group.transpose_fwd()
     tk = _tick("a2a_fwd", tk)
@@ -378,7 +460,17 @@ def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_ite
         R.ext(R.hB, 1, 0.0, epsl, zt=R.ztB, nyh_override=R.kyn, ky_off=R.ky0, nyh_tab=R.nyh)
     tk = _tick("B", tk)
     group.transpose_bwd()
-    tk = _tick("a2a_bwd", tk)
+    return _tick("a2a_bwd", tk)
+
+  it = 0
+  for it in range(n_maxiter):
+    tk = None
+    if prof:
+      t.cuda.synchronize()
+      tk = time.perf_counter()
+    if front_for != ranks[0].cd:
+      tk = front(ranks[0].cd, tk)
+    front_for = None
     for R in ranks:
       # phase C of the local handle normalises the inverse transforms by 1 / (nxp ny); the x-transform ran over the global nx
       R.ext(R.hL, 2, tau * R.nxp / R.nx, epsl, zt=R.zt, phi_in=R.phi[R.cp], phi_out=R.phi[R.cp ^ 1], phib=R.phib)
@@ -391,15 +483,14 @@ def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_ite
     f1, f2 = (cd + 1) % 3, (cd + 2) % 3
     other = lambda b: f2 if b == f1 else f1
 
-    def inner_err(v, b0):
-      with np.errstate(all="ignore"):
-        return v[b0] / v[b0 + 1] + sum(v[b0 + 2 + 2 * q] / v[b0 + 3 + 2 * q] for q in range(4))
-
     def first_hit(v, ns):
-      for sw in range(ns):
-        if inner_err(v, 0 if sw == 0 else 20 + 16 * (sw - 1)) < eps:
-          return sw
-      return -1
+      """First sweep of a pass whose relative change (update_fns_in_pdhg.py:170-177: rho term + the four control terms) is below
+      eps, or -1.  (Vectorised over the sweeps; the five ratios are added in the order of the scalar expression.)"""
+      with np.errstate(all="ignore"):
+        r = v[_NUM[:ns]] / v[_DEN[:ns]]
+        e = r[:, 0] + (((r[:, 1] + r[:, 2]) + r[:, 3]) + r[:, 4])
+      h = np.flatnonzero(e < eps)
+      return int(h[0]) if h.size else -1
 
     def last_sweep_sums(v, ns):          # v[0..15] <- the sums of sweep ns of a fused pass
       if ns > 1:
@@ -433,7 +524,13 @@ def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_ite
       if j > 1:
         e_pass(last, len(plan))
       tk = _tick("D_pass", tk)
-      V = group.allreduce_sums(len(plan) + 1)
+      tok = group.sums_begin(len(plan) + 1)
+      if ahead and it + 1 < n_maxiter:
+        # the host's read of the sums and its decisions take ~0.1 ms during which the stream would run dry: the first half of
+        # the NEXT iteration (it touches nothing this iteration could still need: zt, ztB, ghost rows) is enqueued first
+        front(last)
+        front_for = last
+      V = group.sums_end(tok)
       tk = _tick("allreduce", tk)
       jj, hit_at = 0, -1
       for p, ns in enumerate(plan):
@@ -452,6 +549,7 @@ def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_ite
           d_rho, d_alp = vo[10], [vo[11 + q] for q in range(4)]
       else:
         n_respec += 1
+        front_for = None
         if n_respec > 8 and 4 * n_respec > it:       # the sweep count keeps changing: the prediction does not pay on this problem
           spec = False
     if not done_spec:
@@ -492,6 +590,8 @@ def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_ite
           err2 += ne
         elif na >= 1e-6:
           err2 += ne / na
+    if trace:
+      print("slab it %d err1 %.17g err2 %.17g sweeps %d spec %s" % (it, err1, err2, j, done_spec), flush=True)
     S_rho, S_alp = v[1], np.array([v[3 + 2 * q] for q in range(4)])
     for R in ranks:
       R.cp ^= 1
