@@ -194,7 +194,7 @@ extern "C" int pdhg_max_fuse(pdhg_handle* h) {
 
 extern "C" int pdhg_ext_phase(pdhg_handle* h, int phase, int pass_mask, double step, double epsl, const pdhg_ext_buffers* bufs,
                               int sum_lo, int sum_hi, int nyh_override, int ky_off, int nyh_tab, void* stream) {
-  if (!h || !bufs || phase < 0 || phase > 4) return fail(PDHG_ERR_ARG, "pdhg_ext_phase: bad argument");
+  if (!h || !bufs || phase < 0 || phase > 5) return fail(PDHG_ERR_ARG, "pdhg_ext_phase: bad argument");   // 5: empty launch (diagnostic)
   if (h->B != 1) return fail(PDHG_ERR_ARG, "pdhg_ext_phase: slab mode needs a handle with batch = 1");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   DeviceGuard guard(h->cfg.device);

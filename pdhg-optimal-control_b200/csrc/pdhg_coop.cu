@@ -1615,6 +1615,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pdhg_coop_kernel() {
     // phase as its own launch.  Results are not meaningful; nothing outside the workspace is written.
     double v[kNV];
     switch (a.dbg_phase) {
+      case 5: return;                          // diagnostic: the fixed cost of a launch (argument block, context set-up, exit)
       case 0: run_A(c, 0, epsl); break;
       case 1: phase_B(c); break;
       case 2: run_C(c, w.phi[0], w.phi[1], w.phib, a.op_step); break;

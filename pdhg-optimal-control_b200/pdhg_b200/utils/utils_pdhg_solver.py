@@ -315,7 +315,7 @@ def PDHG_multi_step(fn_update_primal, fn_update_dual, fns_dict, g, x_arr,
   if info is not None:
     info.update(block_iters=logs.iters[0, :done].tolist(), stepsz_used=logs.stepsz_used[0, :done].tolist(), sol_nan=sol_nan,
                 stepsz_final=float(logs.stepsz_final[0]), n_inner=int(logs.inner_total[0]), blocks_done=done,
-                path=s.path, launches=s.launch_count)
+                path=s.path, launches=s.launch_count, kernel_ms=s.last_kernel_ms)
   if done == 0:
     # the reference raises in jnp.concatenate([]) here (utils_pdhg_solver.py:215); report the failure instead
     print('pdhg does not conv, please decrease stepsize to be less than {}'.format(float(logs.stepsz_final[0])), flush=True)

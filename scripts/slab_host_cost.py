@@ -24,6 +24,7 @@ pieces = {
   "D2": lambda: R.ext(R.hL, 3, sigma, epsl, pass_mask=2, phib=R.phib, rho_in=R.rho[0], alp_in=R.alp[0], rho_out=R.rho[1], alp_out=R.alp[1], sums=R.sums[0]),
   "D%d" % R.fuse: lambda: R.ext(R.hL, 3, sigma, epsl, pass_mask=R.fuse, phib=R.phib, rho_in=R.rho[0], alp_in=R.alp[0], rho_out=R.rho[1], alp_out=R.alp[1], sums=R.sums[0]),
   "E": lambda: R.ext(R.hL, 4, 0.0, epsl, rho_in=R.rho[0], alp_in=R.alp[0], rho_out=R.rho[1], alp_out=R.alp[1], sums=R.sums[1]),
+  "empty_launch": lambda: R.ext(R.hL, 5, 0.0, epsl),
   "halo_dual": lambda: grp.halo(lambda r: [r.dual[0][0:3]]),
   "halo_phib": lambda: grp.halo(lambda r: [r.phib]),
   "transpose_fwd": grp.transpose_fwd,
