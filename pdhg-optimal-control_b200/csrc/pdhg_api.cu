@@ -20,6 +20,7 @@ cudaError_t launch_pdhg_coop(const MarchParams& p, int B, void* ws, cudaStream_t
 size_t pdhg_coop_workspace_bytes(const MarchParams& p, int B);
 cudaError_t coop_phase_times(const MarchParams& p, void* ws, double* out6);
 int coop_max_fuse(const MarchParams& p);
+int coop_exchange_ok(const MarchParams& p);
 cudaError_t launch_ext_phase(const MarchParams& p, void* ws, int phase, int pass_mask, double step, const ExtPhaseDesc& ext,
                              cudaStream_t stream);
 cudaError_t launch_debug_phase(const MarchParams& p, void* ws, int phase, int pass_mask, double step, cudaStream_t stream);
@@ -83,6 +84,8 @@ struct pdhg_handle {
   double* dbg_ns = nullptr;
   double ext_epsl = 0.0;
   bool ext_epsl_set = false;
+  int xch_P = 0, xch_rank = 0, xch_nxl = 0, xch_kyl = 0, xch_nyh = 0;     // fused transposes of the slab mode (pdhg_ext_set_exchange)
+  void* xch_ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   Knobs knobs{};              // diagnostic environment knobs, read once in pdhg_create
   int max_radix = 16;
   void* ws = nullptr;         // cooperative-kernel workspace
@@ -210,8 +213,34 @@ extern "C" int pdhg_ext_phase(pdhg_handle* h, int phase, int pass_mask, double s
   e.phi_in = bufs->phi_in; e.phi_out = bufs->phi_out; e.phib = bufs->phib; e.rho_in = bufs->rho_in; e.alp_in = bufs->alp_in;
   e.rho_out = bufs->rho_out; e.alp_out = bufs->alp_out; e.zt = bufs->zt; e.sums = bufs->sums;
   e.sum_lo = sum_lo; e.sum_hi = sum_hi; e.nyh_override = nyh_override; e.ky_off = ky_off; e.nyh_tab = nyh_tab;
+  if (h->xch_P > 0 && phase <= 1) {
+    e.xch_P = h->xch_P; e.xch_rank = h->xch_rank; e.xch_nxl = h->xch_nxl; e.xch_kyl = h->xch_kyl; e.xch_nyh = h->xch_nyh;
+    for (int d = 0; d < 8; ++d) e.xch_ptr[d] = h->xch_ptr[d];
+  }
   CU(launch_ext_phase(p, h->ws, phase, pass_mask, step, e, s));
   h->launches += 1;
+  return PDHG_OK;
+}
+
+extern "C" int pdhg_ext_exchange_ok(pdhg_handle* h) {
+  if (!h) return 0;
+  DeviceGuard guard(h->cfg.device);
+  if (!guard.ok()) return 0;
+  MarchParams p;
+  fill_params(h, &p);
+  return (h->B == 1) ? coop_exchange_ok(p) : 0;
+}
+
+extern "C" int pdhg_ext_set_exchange(pdhg_handle* h, int P, int rank, int nxl, int kyl, int nyh, void* const* peer_ptrs) {
+  if (!h) return fail(PDHG_ERR_ARG, "pdhg_ext_set_exchange: null handle");
+  if (P == 0) { h->xch_P = 0; return PDHG_OK; }
+  if (P < 1 || P > 8 || rank < 0 || rank >= P || nxl < 1 || kyl < 1 || nyh < 1 || !peer_ptrs)
+    return fail(PDHG_ERR_ARG, "pdhg_ext_set_exchange: bad argument (1 <= P <= 8)");
+  if (!pdhg_ext_exchange_ok(h))
+    return fail(PDHG_ERR_UNSUPPORTED, "pdhg_ext_set_exchange: needs a 2-D periodic handle with K = 1 and batch = 1 whose transforms run the generic variants");
+  for (int d = 0; d < P; ++d) if (!peer_ptrs[d]) return fail(PDHG_ERR_ARG, "pdhg_ext_set_exchange: null peer pointer");
+  h->xch_P = P; h->xch_rank = rank; h->xch_nxl = nxl; h->xch_kyl = kyl; h->xch_nyh = nyh;
+  for (int d = 0; d < 8; ++d) h->xch_ptr[d] = (d < P) ? peer_ptrs[d] : nullptr;
   return PDHG_OK;
 }
 

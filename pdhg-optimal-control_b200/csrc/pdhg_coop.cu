@@ -73,6 +73,12 @@ struct CoopArgs {
   int sum_lo, sum_hi;        // x-rows that contribute to the error sums (slab mode: ghost rows excluded); default [0, nxe)
   int ky_off, nyh_tab;       // phase B on an exchanged ky-slab: offset and row length of the per-mode table; default 0, nyh
   double* ext_sums;          // MODE_PHASE: device array [kNV = 20] receiving the grid totals of phases D / E (may be null)
+  // MODE_PHASE, slab mode with fused transposes: xch_on = 1 (phase A): the spectrum value of (ky, local x-row i) goes to rank d = ky / kyl,
+  // slab row ky - d kyl, column rank * nxl + i - 1 of its [kyl][nx_global] ky-slab; xch_on = 2 (phase B on a ky-slab): the value of
+  // (slab row t, global column x) goes to rank d = x / nxl, row ky_off + t, column 1 + x - d nxl of its [nyh][nxl + 2] spectrum
+  int xch_on, xch_rank, xch_nxl, xch_kyl, xch_nyh;
+  int xch_ld;                // row length of the destination: P nxl (forward), nxl + 2 (backward)
+  double2* xch_ptr[8];
   int dbg_phase, dbg_pass;   // MODE_PHASE (profiling): phase id 0..3 = A,B,C,D and pass mask of phase B (bit 0,1,2)
   int tma_d;          // 1: dual sweep through the TMA row pipeline (phase_D_tma); tma_R rows per tile, tma_S ring stages at most
   int tma_R, tma_S;
@@ -466,7 +472,20 @@ __device__ __noinline__ void phase_A(Ctx& c, int cd, double epsl) {
       const int kym = (ky == 0) ? 0 : ny - ky;
       const double2 z1 = zf[(size_t)pr * ld + fpad(ky)], z2 = zf[(size_t)pr * ld + fpad(kym)];
       const int ra = r0 + 2 * pr, ka = fast_div_exact(ra, nx, cargs().inv_nx), ia = ra - ka * nx;
-      stg2(&ztg[((size_t)ka * nyh + ky) * nx + ia], make_double2(0.5 * (z1.x + z2.x), 0.5 * (z1.y - z2.y)));
+      const double2 va = make_double2(0.5 * (z1.x + z2.x), 0.5 * (z1.y - z2.y));
+      if (a.xch_on == 1) {
+        // fused forward transpose: interior x-rows go straight into the owner rank's ky-slab (peer memory); ghost rows are dropped
+        const int d = ky / a.xch_kyl;
+        double2* base = as_global(a.xch_ptr[d]) + (size_t)(ky - d * a.xch_kyl) * (size_t)a.xch_ld + (size_t)a.xch_rank * a.xch_nxl - 1;
+        const size_t kstr = (size_t)a.xch_kyl * (size_t)a.xch_ld;
+        if (ia >= 1 && ia <= a.xch_nxl) stg2(base + (size_t)ka * kstr + ia, va);
+        if (2 * pr + 1 < nrows) {
+          const int rb = ra + 1, kb = fast_div_exact(rb, nx, cargs().inv_nx), ib = rb - kb * nx;
+          if (ib >= 1 && ib <= a.xch_nxl) stg2(base + (size_t)kb * kstr + ib, make_double2(0.5 * (z1.y + z2.y), 0.5 * (z2.x - z1.x)));
+        }
+        continue;
+      }
+      stg2(&ztg[((size_t)ka * nyh + ky) * nx + ia], va);
       if (2 * pr + 1 < nrows) {
         const int rb = ra + 1, kb = fast_div_exact(rb, nx, cargs().inv_nx), ib = rb - kb * nx;
         stg2(&ztg[((size_t)kb * nyh + ky) * nx + ib], make_double2(0.5 * (z1.y + z2.y), 0.5 * (z2.x - z1.x)));
@@ -1028,6 +1047,18 @@ __device__ __noinline__ void phase_B(Ctx& c) {
       }
       __syncthreads();
       zf = fft_rows(zf, zo, a.plan_xe, ld, c.twx(), nr, -1.0);
+    }
+    if (a.xch_on == 2) {
+      // fused backward transpose (uncoupled modes only: K = 1): column x of this ky-slab goes straight into the x-slab of its owner
+      const float inv_nxl = 1.0f / (float)a.xch_nxl;
+      for (int idx = tid; idx < nr * nx; idx += nth) {
+        const int t = fast_div_exact(idx, nx, cargs().inv_nx), kx = idx - t * nx;
+        const int d = fast_div_exact(kx, a.xch_nxl, inv_nxl);
+        stg2(as_global(a.xch_ptr[d]) + ((size_t)k * a.xch_nyh + a.ky_off + ky0 + t) * (size_t)a.xch_ld + 1 + (kx - d * a.xch_nxl),
+             zf[(size_t)t * ld + fpad(kx)]);
+      }
+      __syncthreads();
+      continue;
     }
     for (int idx = tid; idx < nr * nx; idx += nth) {
       const int t = fast_div_exact(idx, nx, cargs().inv_nx), kx = idx - t * nx;
@@ -2013,6 +2044,12 @@ static void apply_ext(const ExtPhaseDesc& e, CoopArgs& a) {
   if (e.zt) a.w.zt = static_cast<double2*>(e.zt);
   a.sum_lo = e.sum_lo; a.sum_hi = e.sum_hi;
   if (e.nyh_override > 0) { a.nyh = e.nyh_override; a.ky_off = e.ky_off; a.nyh_tab = e.nyh_tab; a.b_slab = 0; }
+  if (e.xch_P > 0 && (a.dbg_phase == 0 || a.dbg_phase == 1)) {
+    a.xch_on = (a.dbg_phase == 0) ? 1 : 2;
+    a.xch_rank = e.xch_rank; a.xch_nxl = e.xch_nxl; a.xch_kyl = e.xch_kyl; a.xch_nyh = e.xch_nyh;
+    a.xch_ld = (a.dbg_phase == 0) ? e.xch_P * e.xch_nxl : e.xch_nxl + 2;
+    for (int d = 0; d < 8; ++d) a.xch_ptr[d] = static_cast<double2*>(e.xch_ptr[d]);
+  }
 }
 
 static cudaError_t coop_launch(const MarchParams& p, void* ws, int b, int mode, const double* op_in, double* op_out,
@@ -2094,6 +2131,17 @@ int coop_max_fuse(const MarchParams& p) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   return coop_geom(p, sms, ((size_t)smem_cap - 4096) / kCtasPerSm - (kCtasPerSm > 1 ? 2048 : 0)).d_fuse_ext;
+}
+
+// 1 if phases A and B of this problem run their generic (shared-memory tile) variants, the ones that can scatter their output
+// into other ranks' buffers (fused transposes of the slab mode); the warp-private 256-point variants cannot
+int coop_exchange_ok(const MarchParams& p) {
+  int dev = 0, sms = 0, smem_cap = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const CoopGeom g = coop_geom(p, sms, ((size_t)smem_cap - 4096) / kCtasPerSm - (kCtasPerSm > 1 ? 2048 : 0));
+  return (p.ndim == 2 && p.K == 1 && !g.fast_x && !g.fast_y && p.bc_x == 0) ? 1 : 0;
 }
 
 cudaError_t coop_phase_times(const MarchParams& p, void* ws, double* out6) {

@@ -19,7 +19,7 @@ LOG_COLS = 4
 
 EXPORTS = ("pdhg_create", "pdhg_destroy", "pdhg_last_error", "pdhg_path", "pdhg_launch_count", "pdhg_last_kernel_ms", "pdhg_phase_times", "pdhg_debug_phase", "pdhg_ext_phase", "pdhg_update_primal",
            "pdhg_update_dual", "pdhg_solve_block", "pdhg_multi_step", "pdhg_multi_step_host", "pdhg_multi_step_range", "pdhg_get_march_state",
-           "pdhg_set_march_state", "pdhg_compute_traj", "pdhg_max_fuse")
+           "pdhg_set_march_state", "pdhg_compute_traj", "pdhg_max_fuse", "pdhg_ext_exchange_ok", "pdhg_ext_set_exchange")
 
 
 class PdhgError(RuntimeError):
@@ -94,6 +94,10 @@ def load():
   lib.pdhg_set_march_state.argtypes = [vp, dp, dp, dp, vp]
   lib.pdhg_max_fuse.restype = C.c_int
   lib.pdhg_max_fuse.argtypes = [vp]
+  lib.pdhg_ext_exchange_ok.restype = C.c_int
+  lib.pdhg_ext_exchange_ok.argtypes = [vp]
+  lib.pdhg_ext_set_exchange.restype = C.c_int
+  lib.pdhg_ext_set_exchange.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
   lib.pdhg_compute_traj.restype = C.c_int
   lib.pdhg_compute_traj.argtypes = [i32] * 10 + [dbl, dbl, dbl] + [dp] * 8 + [vp]
   lib.pdhg_multi_step_host.restype = C.c_int
@@ -198,6 +202,16 @@ class Solver:
     eb = ExtBuffers(*[bufs.get(f[0]) for f in ExtBuffers._fields_])
     _check(self.lib.pdhg_ext_phase(self._h, int(phase), int(pass_mask), float(step), float(epsl), C.byref(eb), int(sum_lo), int(sum_hi),
                                    int(nyh_override), int(ky_off), int(nyh_tab), stream))
+
+  @property
+  def exchange_ok(self):
+    return bool(self.lib.pdhg_ext_exchange_ok(self._h))
+
+  def set_exchange(self, P, rank, nxl, kyl, nyh, ptrs):
+    """Fused transposes of the slab mode (pdhg_ext_set_exchange): `ptrs[d]` = device pointer (int) of rank d's destination buffer as
+    seen from this device; P = 0 switches the scatter off."""
+    arr = (C.c_void_p * 8)(*([int(p) for p in ptrs] + [None] * (8 - len(ptrs)))) if P else None
+    _check(self.lib.pdhg_ext_set_exchange(self._h, int(P), int(rank), int(nxl), int(kyl), int(nyh), arr))
 
   @property
   def max_fuse(self):

@@ -93,12 +93,36 @@ class SlabRank:
     h.ext_phase(phase, step, epsl, 1, self.nxl + 1, stream=self._stream, **extra, **ptr)
 
 
+def _fused_default():
+  """Which transposes are fused into the producing kernel (pdhg_ext_set_exchange): "bwd" (default), "both" or "0" (env
+  PDHG_SLAB_FUSED_XCH).  Backward: phase B stores whole rows of nxl values into the owners' x-slabs - efficient over NVLink, and the
+  copy kernels + their launches disappear (2048^2, P = 2: 43 -> 18 us).  Forward: phase A's transposed store reaches a remote ky-slab
+  in 32-96-byte pieces, which slows A by more than the copy it saves (A 89 -> 121 us for 45 -> 26 us), hence opt-in."""
+  return os.environ.get("PDHG_SLAB_FUSED_XCH", "bwd")
+
+
+def _set_exchange(ranks, fwd_ptr, bwd_ptr, mode):
+  """Fused transposes: phase B of every rank scatters its result straight back into the ranks' x-slabs (`bwd_ptr(R, d)` = rank d's zt as
+  seen from R's device); with mode "both" phase A also scatters its half spectrum straight into the ranks' ky-slabs (`fwd_ptr`).
+  Returns (fused_fwd, fused_bwd); (False, False) if the handles' transforms cannot scatter (warp-private 256-point variants)."""
+  mode = {True: "both", False: "0", None: "0", "1": "bwd"}.get(mode, mode)
+  if mode not in ("bwd", "both") or not all(hasattr(R, "hL") and R.hL.exchange_ok and R.hB.exchange_ok for R in ranks):
+    return False, False
+  for R in ranks:
+    if mode == "both":
+      R.hL.set_exchange(R.P, R.rank, R.nxl, R.kyl, R.nyh, [fwd_ptr(R, d) for d in range(R.P)])
+    R.hB.set_exchange(R.P, R.rank, R.nxl, R.kyl, R.nyh, [bwd_ptr(R, d) for d in range(R.P)])
+  return mode == "both", True
+
+
 class LocalGroup:
   """P emulated ranks in one process / on one GPU: collectives are tensor copies (used for parity tests)."""
 
-  def __init__(self, ranks):
+  def __init__(self, ranks, fused=None):
     self.ranks = ranks
     self.P = len(ranks)
+    self.fused_fwd, self.fused_bwd = _set_exchange(ranks, lambda R, d: ranks[d].ztB.data_ptr(), lambda R, d: ranks[d].zt.data_ptr(),
+                                                   _fused_default() if fused is None else fused)
 
   def halo(self, get, fenced=False):
     P = self.P
@@ -108,6 +132,8 @@ class LocalGroup:
         a[..., R.nxl + 1, :] = right[..., 1, :]
 
   def transpose_fwd(self):
+    if self.fused_fwd:        # phase A stored its spectrum straight into the ranks' ky-slabs
+      return
     t = _dev.torch()
     P, R0 = self.P, self.ranks[0]
     K, kyl, nxl, nyh = R0.K, R0.kyl, R0.nxl, R0.nyh
@@ -121,6 +147,8 @@ class LocalGroup:
       R.ztB.copy_(recv.permute(1, 2, 0, 3).reshape(K, kyl, P * nxl))
 
   def transpose_bwd(self):
+    if self.fused_bwd:
+      return
     t = _dev.torch()
     P, R0 = self.P, self.ranks[0]
     K, kyl, nxl, nyh = R0.K, R0.kyl, R0.nxl, R0.nyh
@@ -155,6 +183,7 @@ class DistGroup:
     self.ranks = [rank_state]
     self.dist = dist
     self.P = dist.get_world_size()
+    self.fused_fwd = self.fused_bwd = False
 
   def halo(self, get, fenced=False):
     """Ghost rows of every array `get(R)` returns, ONE message per neighbour: the boundary rows of all arrays are packed into
@@ -253,6 +282,10 @@ class SymmGroup(DistGroup):
     self.base = rank_state.arena.storage_offset()
     self.set = 0
     self._cache = {}
+    R = rank_state
+    zb, zr = t.view_as_real(R.ztB), t.view_as_real(R.zt)
+    self.fused_fwd, self.fused_bwd = _set_exchange([R], lambda R_, d: self._peer(zb, d).data_ptr(), lambda R_, d: self._peer(zr, d).data_ptr(),
+                                                   _fused_default())
     self.side = t.cuda.Stream(device=rank_state.dev)
     self.ev_main, self.ev_side = t.cuda.Event(), t.cuda.Event()
 
@@ -299,6 +332,9 @@ class SymmGroup(DistGroup):
 
   def transpose_fwd(self):
     R, P = self.ranks[0], self.P
+    if self.fused_fwd:        # phase A stored its spectrum straight into the peers' ky-slabs: only the barrier is left
+      self.hdl.barrier()
+      return
 
     def build():
       t = _dev.torch()
@@ -318,6 +354,9 @@ class SymmGroup(DistGroup):
 
   def transpose_bwd(self):
     R, P = self.ranks[0], self.P
+    if self.fused_bwd:        # phase B stored its result straight into the peers' x-slabs
+      self.hdl.barrier()
+      return
 
     def build():
       t = _dev.torch()
