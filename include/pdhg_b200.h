@@ -127,17 +127,23 @@ typedef struct pdhg_ext_buffers {
 int pdhg_max_fuse(pdhg_handle* h);
 int pdhg_ext_phase(pdhg_handle* h, int phase, int pass_mask, double step, double epsl, const pdhg_ext_buffers* bufs,
                    int sum_lo, int sum_hi, int nyh_override, int ky_off, int nyh_tab, void* stream);
-/* Slab mode, fused transposes (compute + exchange in one kernel over peer memory).  After pdhg_ext_set_exchange(h, P, rank, nxl, kyl,
- * nyh, ptrs), phase 0 run through `h` (the rank's local handle: nx = nxl + 2 rows incl. one ghost row per side) no longer writes
- * bufs->zt: the half-spectrum value of (ky, local row i in 1..nxl) is stored straight into rank d = ky / kyl's ky-slab
- * ptrs[d][ky - d kyl][rank nxl + i - 1] (a [kyl][P nxl] complex array per rank); phase 1 run through `h` (the handle of the global
- * x-extent, on this rank's ky-slab: nyh_override rows starting at ky_off) stores the value of (slab row t, column x) straight into
- * rank d = x / nxl's spectrum ptrs[d][ky_off + t][1 + x - d nxl] (a [nyh][nxl + 2] complex array per rank).  ptrs[d] are device
- * pointers valid on THIS device: the rank's own buffer, peer-mapped buffers of the other ranks (CUDA VMM / symmetric memory), or
- * plain buffers when several ranks are emulated on one GPU.  The caller still separates the phases with a barrier across the ranks.
- * P = 0 switches the scatter off again.  pdhg_ext_exchange_ok: 1 if the handle's transforms can scatter (generic variants, K = 1). */
+/* Slab mode, fused transposes (compute + exchange in ONE kernel over peer memory).  The half spectrum of the grid is a distributed
+ * array [nyh][P nxl]: rank d holds columns [d nxl, (d + 1) nxl) of all rows as columns 1..nxl of its [nyh][nxl + 2] array `zt`.
+ *  - phase 1 through a handle of the global x-extent, on this rank's ky-slab (nyh_override rows starting at ky_off), after
+ *    pdhg_ext_set_exchange(h, P, rank, nxl, kyl, nyh, gather, ptrs) with ptrs[d] = rank d's `zt`: the result of (slab row t, column x) is
+ *    stored straight into its owner's array, ptrs[x / nxl][ky_off + t][1 + x mod nxl], instead of bufs->zt; with gather != 0 the input
+ *    rows are also loaded straight from there (bufs->zt is then not touched at all: all-gather -> transform / solve -> scatter in one
+ *    kernel, the rank reads and writes only the rows of its own ky range);
+ *  - phase 0 through the rank's local handle (nx = nxl + 2 rows incl. one ghost row per side) after pdhg_ext_set_exchange with
+ *    ptrs[d] = rank d's ky-slab buffer ([kyl][P nxl] complex): the value of (ky, local row i in 1..nxl) is stored straight into
+ *    ptrs[ky / kyl][ky mod kyl][rank nxl + i - 1] instead of bufs->zt (32-96-byte pieces: slower than a copy over NVLink; for
+ *    emulation and measurement).
+ * ptrs[d] are device pointers valid on THIS device: the rank's own buffer, peer-mapped buffers of the other ranks (CUDA VMM /
+ * symmetric memory), or plain buffers when several ranks are emulated on one GPU.  The caller still separates the phases with a
+ * barrier across the ranks.  P = 0 switches the exchange off again.  pdhg_ext_exchange_ok: 1 if the handle's transforms can do this
+ * (generic variants, K = 1, periodic). */
 int pdhg_ext_exchange_ok(pdhg_handle* h);
-int pdhg_ext_set_exchange(pdhg_handle* h, int P, int rank, int nxl, int kyl, int nyh, void* const* peer_ptrs);
+int pdhg_ext_set_exchange(pdhg_handle* h, int P, int rank, int nxl, int kyl, int nyh, int gather, void* const* peer_ptrs);
 
 /* diagnostic (profiling aid): launches ONE phase of the cooperative kernel `reps` times on the workspace left by the last
  * march, so that ncu sees each phase as its own launch: phase 0 = A, 1 = B (pass_mask bit 0/1/2 = x-FFT / t-solve / inverse

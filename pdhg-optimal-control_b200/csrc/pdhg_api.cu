@@ -84,7 +84,7 @@ struct pdhg_handle {
   double* dbg_ns = nullptr;
   double ext_epsl = 0.0;
   bool ext_epsl_set = false;
-  int xch_P = 0, xch_rank = 0, xch_nxl = 0, xch_kyl = 0, xch_nyh = 0;     // fused transposes of the slab mode (pdhg_ext_set_exchange)
+  int xch_P = 0, xch_rank = 0, xch_nxl = 0, xch_kyl = 0, xch_nyh = 0, xch_pull = 0;     // fused transposes of the slab mode (pdhg_ext_set_exchange)
   void* xch_ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   Knobs knobs{};              // diagnostic environment knobs, read once in pdhg_create
   int max_radix = 16;
@@ -214,7 +214,7 @@ extern "C" int pdhg_ext_phase(pdhg_handle* h, int phase, int pass_mask, double s
   e.rho_out = bufs->rho_out; e.alp_out = bufs->alp_out; e.zt = bufs->zt; e.sums = bufs->sums;
   e.sum_lo = sum_lo; e.sum_hi = sum_hi; e.nyh_override = nyh_override; e.ky_off = ky_off; e.nyh_tab = nyh_tab;
   if (h->xch_P > 0 && phase <= 1) {
-    e.xch_P = h->xch_P; e.xch_rank = h->xch_rank; e.xch_nxl = h->xch_nxl; e.xch_kyl = h->xch_kyl; e.xch_nyh = h->xch_nyh;
+    e.xch_P = h->xch_P; e.xch_rank = h->xch_rank; e.xch_nxl = h->xch_nxl; e.xch_kyl = h->xch_kyl; e.xch_nyh = h->xch_nyh; e.xch_pull = h->xch_pull;
     for (int d = 0; d < 8; ++d) e.xch_ptr[d] = h->xch_ptr[d];
   }
   CU(launch_ext_phase(p, h->ws, phase, pass_mask, step, e, s));
@@ -231,7 +231,7 @@ extern "C" int pdhg_ext_exchange_ok(pdhg_handle* h) {
   return (h->B == 1) ? coop_exchange_ok(p) : 0;
 }
 
-extern "C" int pdhg_ext_set_exchange(pdhg_handle* h, int P, int rank, int nxl, int kyl, int nyh, void* const* peer_ptrs) {
+extern "C" int pdhg_ext_set_exchange(pdhg_handle* h, int P, int rank, int nxl, int kyl, int nyh, int gather, void* const* peer_ptrs) {
   if (!h) return fail(PDHG_ERR_ARG, "pdhg_ext_set_exchange: null handle");
   if (P == 0) { h->xch_P = 0; return PDHG_OK; }
   if (P < 1 || P > 8 || rank < 0 || rank >= P || nxl < 1 || kyl < 1 || nyh < 1 || !peer_ptrs)
@@ -239,7 +239,7 @@ extern "C" int pdhg_ext_set_exchange(pdhg_handle* h, int P, int rank, int nxl, i
   if (!pdhg_ext_exchange_ok(h))
     return fail(PDHG_ERR_UNSUPPORTED, "pdhg_ext_set_exchange: needs a 2-D periodic handle with K = 1 and batch = 1 whose transforms run the generic variants");
   for (int d = 0; d < P; ++d) if (!peer_ptrs[d]) return fail(PDHG_ERR_ARG, "pdhg_ext_set_exchange: null peer pointer");
-  h->xch_P = P; h->xch_rank = rank; h->xch_nxl = nxl; h->xch_kyl = kyl; h->xch_nyh = nyh;
+  h->xch_P = P; h->xch_rank = rank; h->xch_nxl = nxl; h->xch_kyl = kyl; h->xch_nyh = nyh; h->xch_pull = gather ? 1 : 0;
   for (int d = 0; d < 8; ++d) h->xch_ptr[d] = (d < P) ? peer_ptrs[d] : nullptr;
   return PDHG_OK;
 }

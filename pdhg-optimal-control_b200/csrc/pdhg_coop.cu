@@ -78,6 +78,7 @@ struct CoopArgs {
   // (slab row t, global column x) goes to rank d = x / nxl, row ky_off + t, column 1 + x - d nxl of its [nyh][nxl + 2] spectrum
   int xch_on, xch_rank, xch_nxl, xch_kyl, xch_nyh;
   int xch_ld;                // row length of the destination: P nxl (forward), nxl + 2 (backward)
+  int xch_pull;              // xch_on = 2: phase B also GATHERS its input rows from the owners' x-slabs (same pointers)
   double2* xch_ptr[8];
   int dbg_phase, dbg_pass;   // MODE_PHASE (profiling): phase id 0..3 = A,B,C,D and pass mask of phase B (bit 0,1,2)
   int tma_d;          // 1: dual sweep through the TMA row pipeline (phase_D_tma); tma_R rows per tile, tma_S ring stages at most
@@ -995,9 +996,20 @@ __device__ __noinline__ void phase_B(Ctx& c) {
   for (int u = blockIdx.x; u < ((pmask & 1) ? nunits : 0); u += gridDim.x) {
     const int k = u / ntile, ky0 = (u - k * ntile) * TKY;
     const int nr = min(TKY, nyh - ky0);
-    for (int idx = tid; idx < nr * nx; idx += nth) {
-      const int t = fast_div_exact(idx, nx, cargs().inv_nx), kx = idx - t * nx;
-      buf0[(size_t)t * ld + fpad(kx)] = ldg2(&zt[((size_t)k * nyh + ky0 + t) * nx + kx]);
+    if (a.xch_on == 2 && a.xch_pull) {
+      // fused forward transpose: the rows of this ky-slab are gathered straight from the x-slabs of their owners (peer memory)
+      const float inv_nxl = 1.0f / (float)a.xch_nxl;
+      for (int idx = tid; idx < nr * nx; idx += nth) {
+        const int t = fast_div_exact(idx, nx, cargs().inv_nx), kx = idx - t * nx;
+        const int d = fast_div_exact(kx, a.xch_nxl, inv_nxl);
+        buf0[(size_t)t * ld + fpad(kx)] =
+            ldg2(as_global(a.xch_ptr[d]) + ((size_t)k * a.xch_nyh + a.ky_off + ky0 + t) * (size_t)a.xch_ld + 1 + (kx - d * a.xch_nxl));
+      }
+    } else {
+      for (int idx = tid; idx < nr * nx; idx += nth) {
+        const int t = fast_div_exact(idx, nx, cargs().inv_nx), kx = idx - t * nx;
+        buf0[(size_t)t * ld + fpad(kx)] = ldg2(&zt[((size_t)k * nyh + ky0 + t) * nx + kx]);
+      }
     }
     __syncthreads();
     if (p.bc_x == 1) {
@@ -2048,6 +2060,7 @@ static void apply_ext(const ExtPhaseDesc& e, CoopArgs& a) {
     a.xch_on = (a.dbg_phase == 0) ? 1 : 2;
     a.xch_rank = e.xch_rank; a.xch_nxl = e.xch_nxl; a.xch_kyl = e.xch_kyl; a.xch_nyh = e.xch_nyh;
     a.xch_ld = (a.dbg_phase == 0) ? e.xch_P * e.xch_nxl : e.xch_nxl + 2;
+    a.xch_pull = (a.dbg_phase == 1) ? e.xch_pull : 0;
     for (int d = 0; d < 8; ++d) a.xch_ptr[d] = static_cast<double2*>(e.xch_ptr[d]);
   }
 }

@@ -90,7 +90,7 @@ struct ExtPhaseDesc {
   int sum_lo, sum_hi, nyh_override, ky_off, nyh_tab;
   // fused transpose (pdhg_ext_set_exchange): phase 0 scatters the half spectrum straight into the ky-slabs of the P ranks, phase 1 its
   // result straight back into their x-slabs (peer-mapped pointers), instead of writing `zt` for a separate exchange step
-  int xch_P = 0, xch_rank = 0, xch_nxl = 0, xch_kyl = 0, xch_nyh = 0;
+  int xch_P = 0, xch_rank = 0, xch_nxl = 0, xch_kyl = 0, xch_nyh = 0, xch_pull = 0;
   void* xch_ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 

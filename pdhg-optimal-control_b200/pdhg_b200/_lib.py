@@ -97,7 +97,7 @@ def load():
   lib.pdhg_ext_exchange_ok.restype = C.c_int
   lib.pdhg_ext_exchange_ok.argtypes = [vp]
   lib.pdhg_ext_set_exchange.restype = C.c_int
-  lib.pdhg_ext_set_exchange.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+  lib.pdhg_ext_set_exchange.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
   lib.pdhg_compute_traj.restype = C.c_int
   lib.pdhg_compute_traj.argtypes = [i32] * 10 + [dbl, dbl, dbl] + [dp] * 8 + [vp]
   lib.pdhg_multi_step_host.restype = C.c_int
@@ -207,11 +207,11 @@ class Solver:
   def exchange_ok(self):
     return bool(self.lib.pdhg_ext_exchange_ok(self._h))
 
-  def set_exchange(self, P, rank, nxl, kyl, nyh, ptrs):
-    """Fused transposes of the slab mode (pdhg_ext_set_exchange): `ptrs[d]` = device pointer (int) of rank d's destination buffer as
-    seen from this device; P = 0 switches the scatter off."""
+  def set_exchange(self, P, rank, nxl, kyl, nyh, ptrs, gather=False):
+    """Fused transposes of the slab mode (pdhg_ext_set_exchange): `ptrs[d]` = device pointer (int) of rank d's buffer as seen from this
+    device; `gather`: phase 1 also loads its input rows from there; P = 0 switches the exchange off."""
     arr = (C.c_void_p * 8)(*([int(p) for p in ptrs] + [None] * (8 - len(ptrs)))) if P else None
-    _check(self.lib.pdhg_ext_set_exchange(self._h, int(P), int(rank), int(nxl), int(kyl), int(nyh), arr))
+    _check(self.lib.pdhg_ext_set_exchange(self._h, int(P), int(rank), int(nxl), int(kyl), int(nyh), int(bool(gather)), arr))
 
   @property
   def max_fuse(self):

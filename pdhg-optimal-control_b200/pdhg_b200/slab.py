@@ -94,25 +94,27 @@ class SlabRank:
 
 
 def _fused_default():
-  """Which transposes are fused into the producing kernel (pdhg_ext_set_exchange): "bwd" (default), "both" or "0" (env
-  PDHG_SLAB_FUSED_XCH).  Backward: phase B stores whole rows of nxl values into the owners' x-slabs - efficient over NVLink, and the
-  copy kernels + their launches disappear (2048^2, P = 2: 43 -> 18 us).  Forward: phase A's transposed store reaches a remote ky-slab
-  in 32-96-byte pieces, which slows A by more than the copy it saves (A 89 -> 121 us for 45 -> 26 us), hence opt-in."""
-  return os.environ.get("PDHG_SLAB_FUSED_XCH", "bwd")
+  """Which transposes are fused into the producing / consuming kernel (pdhg_ext_set_exchange; env PDHG_SLAB_FUSED_XCH):
+    "B"    (default) phase B GATHERS the rows of its ky-slab straight from the owners' x-slabs and SCATTERS its result straight back:
+           both transposes live inside one kernel, no ky-slab buffer, no copy kernels - only the two barriers remain;
+    "bwd"  phase B scatters only (the forward transpose stays a set of strided peer copies);
+    "both" phase A scatters its half spectrum into the owners' ky-slabs and phase B scatters back (A's transposed store reaches a remote
+           slab in 32-96-byte pieces, which slows A by more than the copy it saves: 2048^2, P = 2: A 89 -> 121 us for 45 -> 26 us);
+    "0"    strided peer copies both ways."""
+  return os.environ.get("PDHG_SLAB_FUSED_XCH", "B")
 
 
 def _set_exchange(ranks, fwd_ptr, bwd_ptr, mode):
-  """Fused transposes: phase B of every rank scatters its result straight back into the ranks' x-slabs (`bwd_ptr(R, d)` = rank d's zt as
-  seen from R's device); with mode "both" phase A also scatters its half spectrum straight into the ranks' ky-slabs (`fwd_ptr`).
-  Returns (fused_fwd, fused_bwd); (False, False) if the handles' transforms cannot scatter (warp-private 256-point variants)."""
-  mode = {True: "both", False: "0", None: "0", "1": "bwd"}.get(mode, mode)
-  if mode not in ("bwd", "both") or not all(hasattr(R, "hL") and R.hL.exchange_ok and R.hB.exchange_ok for R in ranks):
+  """`bwd_ptr(R, d)` = rank d's zt as seen from R's device, `fwd_ptr(R, d)` = rank d's ky-slab buffer ztB.  Returns (fused_fwd,
+  fused_bwd); (False, False) if the handles' transforms cannot do it (warp-private 256-point variants)."""
+  mode = {True: "B", False: "0", None: "0", "1": "B"}.get(mode, mode)
+  if mode not in ("B", "bwd", "both") or not all(hasattr(R, "hL") and R.hL.exchange_ok and R.hB.exchange_ok for R in ranks):
     return False, False
   for R in ranks:
     if mode == "both":
       R.hL.set_exchange(R.P, R.rank, R.nxl, R.kyl, R.nyh, [fwd_ptr(R, d) for d in range(R.P)])
-    R.hB.set_exchange(R.P, R.rank, R.nxl, R.kyl, R.nyh, [bwd_ptr(R, d) for d in range(R.P)])
-  return mode == "both", True
+    R.hB.set_exchange(R.P, R.rank, R.nxl, R.kyl, R.nyh, [bwd_ptr(R, d) for d in range(R.P)], gather=(mode == "B"))
+  return mode in ("both", "B"), True
 
 
 class LocalGroup:

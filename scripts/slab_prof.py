@@ -13,10 +13,11 @@ x_arr = rx.make_x_arr(2, nx, nx, 2.0, 2.0)
 with contextlib.redirect_stdout(io.StringIO()):
   fns = sf.set_up_example_fns(1, 2, 0)
 g = sf.set_up_J(1, 2, (2.0, 2.0))(x_arr)[0]
-for fuse in (2, 5):
+quick = os.environ.get("PDHG_SLAB_PROF_QUICK") is not None
+for fuse in ((5,) if quick else (2, 5)):
   os.environ["PDHG_SLAB_FUSE"] = str(fuse)
   R, grp, kind = slab.make_dist_rank(rank, world, dist, fns, nx, nx, 1.0 / 256, (2.0 / nx, 2.0 / nx), 70.0, x_arr, device=local)
-  for prof in (False, True):
+  for prof in ((False,) if quick else (False, True)):
     if prof: os.environ["PDHG_SLAB_PROF"] = "1"
     else: os.environ.pop("PDHG_SLAB_PROF", None)
     slab.PROFILE.clear()
@@ -27,6 +28,6 @@ for fuse in (2, 5):
     res = slab.solve_block_slab(grp, 0.1, 5e-4, iters)
     torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
     if rank == 0:
-      print(json.dumps({"P": world, "exchange": kind, "fuse_asked": fuse, "fuse": R.fuse, "prof": prof, "ms_per_iter": dt / iters * 1e3, "n_inner": res[4],
+      print(json.dumps({"P": world, "exchange": kind, "fused_transposes": [grp.fused_fwd, grp.fused_bwd], "fuse_asked": fuse, "fuse": R.fuse, "prof": prof, "ms_per_iter": dt / iters * 1e3, "n_inner": res[4],
                         "sections_ms_per_iter": {k: round(v / iters * 1e3, 3) for k, v in slab.PROFILE.items()}}), flush=True)
 dist.destroy_process_group()

@@ -120,9 +120,10 @@ def test_speculative_pass_plan_equals_pass_by_pass_bitwise(built_lib, monkeypatc
 
 @pytest.mark.parametrize("P,nx,ny,epsl,nmax,stepsz", [(2, 32, 24, 0.0, 60, 0.1), (3, 48, 16, 0.1, 60, 0.05), (4, 64, 32, 0.05, 40, 0.05), (4, 24, 512, 0.02, 12, 0.05)])
 def test_fused_transposes_equal_copy_transposes(built_lib, P, nx, ny, epsl, nmax, stepsz):
-  """pdhg_ext_set_exchange: phase B stores its result straight into the ranks' x-slabs ("bwd") and, opt-in, phase A its half spectrum
-  straight into their ky-slabs ("both") - peer pointers; here P emulated ranks on one GPU, incl. a ragged last ky-slab (nyh = ny/2 + 1
-  is not a multiple of P).  "bwd" moves the same values to the same places as the copy transposes: bit-identical iterates.  "both"
+  """pdhg_ext_set_exchange: phase B gathers the rows of its ky-slab straight from the ranks' x-slabs and stores its result straight back
+  ("B", the default; "bwd": stores only) and, opt-in, phase A stores its half spectrum straight into the ranks' ky-slabs ("both") - peer
+  pointers; here P emulated ranks on one GPU, incl. a ragged last ky-slab (nyh = ny/2 + 1 is not a multiple of P).  "B" and "bwd" move
+  the same values as the copy transposes: bit-identical iterates.  "both"
   leaves the ghost columns of the spectrum unwritten, and phase C transforms a ghost row and an interior row as ONE complex row pair,
   so the interior rows next to a ghost row see other rounding noise (amplified by the upwind switches over the iterations): equal
   to the parity tolerance, same iteration count."""
@@ -133,16 +134,17 @@ def test_fused_transposes_equal_copy_transposes(built_lib, P, nx, ny, epsl, nmax
   fns, _ = quiet(sf.set_up_example_fns, 1, 2, 0)
   g = set_up_J(1, 2, (2.0, 2.0))(x_arr)[0]
   out = {}
-  for fused in ("0", "bwd", "both"):
+  for fused in ("0", "bwd", "B", "both"):
     ranks = [slab.SlabRank(r, P, fns, nx, ny, T, (2.0 / nx, 2.0 / ny), 70.0, x_arr) for r in range(P)]
     grp = slab.LocalGroup(ranks, fused=fused)
-    assert (grp.fused_fwd, grp.fused_bwd) == {"0": (False, False), "bwd": (False, True), "both": (True, True)}[fused]
+    assert (grp.fused_fwd, grp.fused_bwd) == {"0": (False, False), "bwd": (False, True), "B": (True, True), "both": (True, True)}[fused]
     slab.init_block(grp, g, 70.0)
     res = slab.solve_block_slab(grp, epsl, stepsz, nmax)
     out[fused] = (res, slab.gather_block(grp))
-  assert out["0"][0] == out["bwd"][0], (out["0"][0], out["bwd"][0])
-  for a, b in zip(out["0"][1], out["bwd"][1]):
-    assert np.array_equal(a, b)
+  for m in ("bwd", "B"):
+    assert out["0"][0] == out[m][0], (m, out["0"][0], out[m][0])
+    for a, b in zip(out["0"][1], out[m][1]):
+      assert np.array_equal(a, b), m
   assert out["0"][0][:2] == out["both"][0][:2] and out["0"][0][4] == out["both"][0][4]
   for a, b in zip(out["0"][1], out["both"][1]):
     assert relmax(a, b) < TOL
