@@ -74,7 +74,10 @@ typedef struct pdhg_config {
   int32_t nblocks;         /* nt_PDHG = (nt-1)/K time blocks (1 for a single block solve) */
   int32_t max_rec;         /* rows reserved per block in the error log (>= 2) */
   int32_t device;          /* CUDA device ordinal */
-  int32_t path;            /* 0 auto | 1 single-CTA shared-memory kernel | 2 cooperative multi-CTA kernel */
+  int32_t path;            /* 0 auto | 1 single-CTA shared-memory kernel | 2 cooperative multi-CTA kernel |
+                            * 3 tables only (ndim 2, K 1, batch 1): per-mode table, twiddles and plans of the grid, NO state and NO
+                            *   workspace - the handle only serves pdhg_ext_phase phase 1 on a caller-owned spectrum (the x-transform
+                            *   handle of the slab decomposition: its memory must not grow with the full grid) */
 } pdhg_config;
 
 /* Host-side logs of a solve; any pointer may be NULL.  Shapes: [B][nblocks] unless noted. */

@@ -199,6 +199,8 @@ extern "C" int pdhg_ext_phase(pdhg_handle* h, int phase, int pass_mask, double s
                               int sum_lo, int sum_hi, int nyh_override, int ky_off, int nyh_tab, void* stream) {
   if (!h || !bufs || phase < 0 || phase > 5) return fail(PDHG_ERR_ARG, "pdhg_ext_phase: bad argument");   // 5: empty launch (diagnostic)
   if (h->B != 1) return fail(PDHG_ERR_ARG, "pdhg_ext_phase: slab mode needs a handle with batch = 1");
+  if (h->path == 3 && !((phase == 1 && (bufs->zt || (h->xch_P > 0 && h->xch_pull))) || phase == 5))
+    return fail(PDHG_ERR_ARG, "pdhg_ext_phase: a tables-only handle (path = 3) runs phase 1 on a caller-owned spectrum only");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   DeviceGuard guard(h->cfg.device);
   if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
@@ -246,6 +248,7 @@ extern "C" int pdhg_ext_set_exchange(pdhg_handle* h, int P, int rank, int nxl, i
 
 extern "C" int pdhg_debug_phase(pdhg_handle* h, int phase, int pass_mask, double step, int reps) {
   if (!h || phase < 0 || phase > 3 || reps < 1) return fail(PDHG_ERR_ARG, "pdhg_debug_phase: bad argument");
+  if (h->path == 3) return fail(PDHG_ERR_ARG, "handle created with path = 3 (tables only): it serves pdhg_ext_phase phase 1 on caller buffers, nothing else");
   DeviceGuard guard(h->cfg.device);
   if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
   MarchParams p;
@@ -305,6 +308,7 @@ extern "C" int pdhg_create(const pdhg_config* cfg, const double* coef_x, const d
   cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device);
   const bool fits1 = (c.ndim == 1) && pdhg1d_cta_smem_bytes(c.nx, c.K) <= (size_t)dev_smem;
   h->path = c.path;
+  if (h->path == 3 && !(c.ndim == 2 && c.batch == 1 && c.K == 1)) { delete h; return fail(PDHG_ERR_ARG, "path 3 (tables only) needs ndim = 2, K = 1, batch = 1"); }
   if (h->path == 0) h->path = fits1 ? 1 : 2;
   if (h->path == 1 && !fits1) { delete h; return fail(PDHG_ERR_ARG, "path 1 (single-CTA) needs 1-D state that fits shared memory"); }
 
@@ -373,9 +377,12 @@ extern "C" int pdhg_create(const pdhg_config* cfg, const double* coef_x, const d
   }
   const size_t B = h->B, NB = (size_t)c.nblocks;
   CB(dalloc(h, &h->epsl, B)); CB(dalloc(h, &h->stepsz, B)); CB(dalloc(h, &h->delta, B)); CB(dalloc(h, &h->floor_, B));
-  CB(dalloc(h, &h->st_phi, B * (c.K + 1) * h->n));
-  CB(dalloc(h, &h->st_rho, B * c.K * h->n));
-  CB(dalloc(h, &h->st_alp, B * h->A * c.K * h->n));
+  const bool tables_only = (h->path == 3);     // slab mode's phase-B handle: per-mode table, twiddles, plans - no state, no workspace
+  if (!tables_only) {
+    CB(dalloc(h, &h->st_phi, B * (c.K + 1) * h->n));
+    CB(dalloc(h, &h->st_rho, B * c.K * h->n));
+    CB(dalloc(h, &h->st_alp, B * h->A * c.K * h->n));
+  }
   CB(dalloc(h, &h->iters, B * NB)); CB(dalloc(h, &h->stepsz_used, B * NB)); CB(dalloc(h, &h->nrec, B * NB));
   CB(dalloc(h, &h->errlog, B * NB * c.max_rec * kLogCols)); CB(dalloc(h, &h->end_reason, B * NB));
   CB(dalloc(h, &h->status, B)); CB(dalloc(h, &h->blocks_done, B)); CB(dalloc(h, &h->inner_total, B));
@@ -383,8 +390,12 @@ extern "C" int pdhg_create(const pdhg_config* cfg, const double* coef_x, const d
   CB(dalloc(h, &h->err_inner, B));
   CB(dalloc(h, &h->dbg_ns, 16));
   CB(cudaMemset(h->dbg_ns, 0, 16 * sizeof(double)));
-  if (c.ndim == 2 && c.n_ctrl > 1) CB(dalloc(h, &h->alp_tmp, B * h->A * c.K * h->n * c.n_ctrl));
-  {
+  if (c.ndim == 2 && c.n_ctrl > 1 && !tables_only) CB(dalloc(h, &h->alp_tmp, B * h->A * c.K * h->n * c.n_ctrl));
+  if (tables_only) {
+    char* w = nullptr;                         // (a token allocation: phase 1 on a caller-owned spectrum touches none of the carved arrays)
+    CB(dalloc(h, &w, 4096));
+    h->ws = w;
+  } else {
     // the cooperative kernel also serves the operator-level entry points, so its workspace always exists
     MarchParams p{};
     p.ndim = c.ndim; p.nx = c.nx; p.ny = c.ny; p.K = c.K;
@@ -497,6 +508,7 @@ extern "C" int pdhg_solve_block(pdhg_handle* h, const double* phi0, const double
                                 double* rho_out, double* alp_out, pdhg_logs* logs, void* stream) {
   if (!h || !phi0 || !rho0 || !alp0 || !stepsz_host || !phi_out || !rho_out || !alp_out)
     return fail(PDHG_ERR_ARG, "pdhg_solve_block: null argument");
+  if (h->path == 3) return fail(PDHG_ERR_ARG, "handle created with path = 3 (tables only): it serves pdhg_ext_phase phase 1 on caller buffers, nothing else");
   if (n_maxiter < 1 || iter_begin < 0 || iter_begin >= n_maxiter) return fail(PDHG_ERR_ARG, "pdhg_solve_block: bad iteration range");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   DeviceGuard guard(h->cfg.device);
@@ -560,6 +572,7 @@ extern "C" int pdhg_multi_step_range(pdhg_handle* h, const double* g_dev, const 
                                      const double* stepsz_cur_host, int64_t n_maxiter, int32_t print_freq, int32_t blk_begin,
                                      int32_t blk_end, double* phi_all, double* rho_all, double* alp_all, pdhg_logs* logs, void* stream) {
   if (!h || !stepsz_host || !phi_all || !rho_all || !alp_all) return fail(PDHG_ERR_ARG, "pdhg_multi_step_range: null argument");
+  if (h->path == 3) return fail(PDHG_ERR_ARG, "handle created with path = 3 (tables only): it serves pdhg_ext_phase phase 1 on caller buffers, nothing else");
   if (n_maxiter < 1) return fail(PDHG_ERR_ARG, "pdhg_multi_step_range: n_maxiter must be >= 1");
   if (blk_begin < 0 || blk_end > h->cfg.nblocks || blk_begin >= blk_end) return fail(PDHG_ERR_ARG, "pdhg_multi_step_range: bad block range");
   if (blk_begin == 0 && !g_dev) return fail(PDHG_ERR_ARG, "pdhg_multi_step_range: g is required when the range starts at block 0");
@@ -572,6 +585,7 @@ extern "C" int pdhg_multi_step_range(pdhg_handle* h, const double* g_dev, const 
 // marching state between time blocks: phi0 of the next block (already warm-started, utils_pdhg_solver.py:200-203), rho0, alp0
 extern "C" int pdhg_get_march_state(pdhg_handle* h, double* phi0, double* rho0, double* alp0, void* stream) {
   if (!h || !phi0 || !rho0 || !alp0) return fail(PDHG_ERR_ARG, "pdhg_get_march_state: null argument");
+  if (h->path == 3) return fail(PDHG_ERR_ARG, "handle created with path = 3 (tables only): it serves pdhg_ext_phase phase 1 on caller buffers, nothing else");
   DeviceGuard guard(h->cfg.device);
   if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -583,6 +597,7 @@ extern "C" int pdhg_get_march_state(pdhg_handle* h, double* phi0, double* rho0, 
 }
 extern "C" int pdhg_set_march_state(pdhg_handle* h, const double* phi0, const double* rho0, const double* alp0, void* stream) {
   if (!h || !phi0 || !rho0 || !alp0) return fail(PDHG_ERR_ARG, "pdhg_set_march_state: null argument");
+  if (h->path == 3) return fail(PDHG_ERR_ARG, "handle created with path = 3 (tables only): it serves pdhg_ext_phase phase 1 on caller buffers, nothing else");
   DeviceGuard guard(h->cfg.device);
   if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -597,6 +612,7 @@ extern "C" int pdhg_multi_step(pdhg_handle* h, const double* g_dev, const double
                                int64_t n_maxiter, int32_t print_freq, double* phi_all, double* rho_all, double* alp_all,
                                pdhg_logs* logs, void* stream) {
   if (!h || !g_dev || !stepsz_host || !phi_all || !rho_all || !alp_all) return fail(PDHG_ERR_ARG, "pdhg_multi_step: null argument");
+  if (h->path == 3) return fail(PDHG_ERR_ARG, "handle created with path = 3 (tables only): it serves pdhg_ext_phase phase 1 on caller buffers, nothing else");
   if (n_maxiter < 1) return fail(PDHG_ERR_ARG, "pdhg_multi_step: n_maxiter must be >= 1");
   DeviceGuard guard(h->cfg.device);
   if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
@@ -609,6 +625,7 @@ extern "C" int pdhg_multi_step_host(pdhg_handle* h, const double* g_host, const 
                                     double* phi_all_host, double* rho_all_host, double* alp_all_host, pdhg_logs* logs) {
   if (!h || !g_host || !stepsz_host || !phi_all_host || !rho_all_host || !alp_all_host)
     return fail(PDHG_ERR_ARG, "pdhg_multi_step_host: null argument");
+  if (h->path == 3) return fail(PDHG_ERR_ARG, "handle created with path = 3 (tables only): it serves pdhg_ext_phase phase 1 on caller buffers, nothing else");
   if (n_maxiter < 1) return fail(PDHG_ERR_ARG, "pdhg_multi_step_host: n_maxiter must be >= 1");
   DeviceGuard guard(h->cfg.device);
   if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
@@ -636,6 +653,7 @@ extern "C" int pdhg_multi_step_host(pdhg_handle* h, const double* g_host, const 
 extern "C" int pdhg_update_primal(pdhg_handle* h, const double* phi_prev, const double* rho_prev, const double* alp_prev,
                                   const double* epsl_host, double tau, double* phi_next, void* stream) {
   if (!h || !phi_prev || !rho_prev || !alp_prev || !phi_next) return fail(PDHG_ERR_ARG, "pdhg_update_primal: null argument");
+  if (h->path == 3) return fail(PDHG_ERR_ARG, "handle created with path = 3 (tables only): it serves pdhg_ext_phase phase 1 on caller buffers, nothing else");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   DeviceGuard guard(h->cfg.device);
   if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");
@@ -656,6 +674,7 @@ extern "C" int pdhg_update_dual(pdhg_handle* h, const double* phi_bar, const dou
                                 const double* epsl_host, double sigma, double eps, double* rho_next, double* alp_next,
                                 int32_t* n_inner_host, double* err_host, void* stream) {
   if (!h || !phi_bar || !rho_prev || !alp_prev || !rho_next || !alp_next) return fail(PDHG_ERR_ARG, "pdhg_update_dual: null argument");
+  if (h->path == 3) return fail(PDHG_ERR_ARG, "handle created with path = 3 (tables only): it serves pdhg_ext_phase phase 1 on caller buffers, nothing else");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   DeviceGuard guard(h->cfg.device);
   if (!guard.ok()) return fail(PDHG_ERR_CUDA, "cudaSetDevice failed");

@@ -49,9 +49,10 @@ class SlabRank:
     # local handle: the padded slab treated as a small periodic problem (its wrap only touches the ghost rows)
     self.hL = _lib.Solver(2, fns_dict.egno, self.nxp, ny, 1, fns_dict.n_ctrl, (0, 0), float(dt), dx, dy, float(c_on_rho), cx[idx], cy,
                           float(C), 1.0, 1.0, float(eps), 10, 1, 1, 4, device, 2)
-    # global handle: owns the per-mode table of the full grid; phase B runs on this rank's ky-slab of it
+    # global handle: owns the per-mode table of the full grid; phase B runs on this rank's ky-slab of it.  path 3 = tables only:
+    # no state and no workspace of the full grid on this rank (a rank's memory must shrink with P)
     self.hB = _lib.Solver(2, fns_dict.egno, nx, ny, 1, fns_dict.n_ctrl, (0, 0), float(dt), dx, dy, float(c_on_rho), cx, cy,
-                          float(C), 1.0, 1.0, float(eps), 10, 1, 1, 4, device, 2)
+                          float(C), 1.0, 1.0, float(eps), 10, 1, 1, 4, device, 3)
     f64 = t.float64
     # every buffer another rank reads or writes is carved from ONE arena (identical layout on all ranks)
     nxp, nyh, kyl = self.nxp, self.nyh, max(self.kyl, 1)

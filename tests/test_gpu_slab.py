@@ -148,3 +148,25 @@ def test_fused_transposes_equal_copy_transposes(built_lib, P, nx, ny, epsl, nmax
   assert out["0"][0][:2] == out["both"][0][:2] and out["0"][0][4] == out["both"][0][4]
   for a, b in zip(out["0"][1], out["both"][1]):
     assert relmax(a, b) < TOL
+
+
+def test_tables_only_handle_rejects_everything_but_phase_b(built_lib):
+  """path = 3 (the slab decomposition's x-transform handle): no state, no workspace of the full grid; every entry point that would
+  need them fails with PDHG_ERR_ARG instead of touching unallocated memory."""
+  import torch
+  from pdhg_b200 import _lib, run_example as rx, set_fns as sf
+  from pdhg_b200.update_fns_in_pdhg import coef_tables
+  nx, ny = 64, 48
+  x_arr = rx.make_x_arr(2, nx, ny, 2.0, 2.0)
+  cx, cy = coef_tables(1, 2, np.asarray(x_arr))
+  h = _lib.Solver(2, 1, nx, ny, 1, 2, (0, 0), 0.05, 2.0 / nx, 2.0 / ny, 70.0, cx, cy, 1.0, 1.0, 1.0, 1e-6, 10, 1, 1, 4, 0, 3)
+  assert h.path == 3
+  zt = torch.zeros((1, ny // 2 + 1, nx), dtype=torch.complex128, device="cuda")
+  h.ext_phase(1, 0.0, 0.0, 0, nx, zt=zt.data_ptr(), nyh_override=ny // 2 + 1, ky_off=0, nyh_tab=ny // 2 + 1)      # phase B runs
+  torch.cuda.synchronize()
+  with pytest.raises(RuntimeError):
+    h.ext_phase(0, 0.0, 0.0, 0, nx, zt=zt.data_ptr())
+  with pytest.raises(RuntimeError):
+    h.debug_phase(1)
+  with pytest.raises(RuntimeError):
+    h.multi_step_host(np.zeros((1, nx, ny)), [0.0], [0.1], 10, 0)
