@@ -459,6 +459,30 @@ def _tick(name, t0):
   return now
 
 
+# slots of the sums of sweep s = 1, 2, .. of a fused pass: [rho, alp 1..4] numerators; the denominators follow each
+_NUM = np.array([[b0 + 2 * q for q in range(5)] for b0 in [0] + [20 + 16 * sw for sw in range((NQ - 20) // 16)]])
+_DEN = _NUM + 1
+
+
+def _first_hit(v, ns, eps):
+  """First sweep (0-based) of a pass of ns fused sweeps whose relative change (update_fns_in_pdhg.py:170-177: rho term + the four
+  control terms) is below eps, or -1.  `v`: the NQ totals of the pass.  (Vectorised over the sweeps; the five ratios are added in
+  the order of the scalar expression  r0 + (((r1 + r2) + r3) + r4), so the result has the bits of the sweep-by-sweep test.)"""
+  with np.errstate(all="ignore"):
+    r = v[_NUM[:ns]] / v[_DEN[:ns]]
+    e = r[:, 0] + (((r[:, 1] + r[:, 2]) + r[:, 3]) + r[:, 4])
+  h = np.flatnonzero(e < eps)
+  return int(h[0]) if h.size else -1
+
+
+def _last_sweep_sums(v, ns):
+  """v with slots 0..15 replaced by the sums of sweep ns of a fused pass (a copy when ns > 1)."""
+  if ns > 1:
+    v = v.copy()
+    v[:16] = v[20 + 16 * (ns - 2):36 + 16 * (ns - 2)]
+  return v
+
+
 def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_iters=10):
   """PDHG_solver_oneiter (utils_pdhg_solver.py:9-94) on the slab-decomposed block.  Returns (iters, end_reason, err1, err2, n_inner)."""
   t = _dev.torch()
@@ -482,8 +506,6 @@ def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_ite
   trace = os.environ.get("PDHG_SLAB_TRACE") is not None and ranks[0].rank == 0
   ahead = spec and not prof and os.environ.get("PDHG_SLAB_AHEAD", "1") != "0"
   front_for = None          # dual buffer for which the first half of the next iteration is already in the stream
-  _NUM = np.array([[b0 + 2 * q for q in range(5)] for b0 in [0] + [20 + 16 * sw for sw in range((NQ - 20) // 16)]])      # [sweep of a pass][rho, alp 1..4]
-  _DEN = _NUM + 1
 
   def front(b, tk=None):
     """First half of an outer iteration on dual buffer b: ghost rows of (rho, alp1_x, alp2_x), continuity residual + y-transform,
@@ -525,20 +547,8 @@ def solve_block_slab(group, epsl, stepsz_param, n_maxiter, eps=1e-6, rho_alp_ite
     f1, f2 = (cd + 1) % 3, (cd + 2) % 3
     other = lambda b: f2 if b == f1 else f1
 
-    def first_hit(v, ns):
-      """First sweep of a pass whose relative change (update_fns_in_pdhg.py:170-177: rho term + the four control terms) is below
-      eps, or -1.  (Vectorised over the sweeps; the five ratios are added in the order of the scalar expression.)"""
-      with np.errstate(all="ignore"):
-        r = v[_NUM[:ns]] / v[_DEN[:ns]]
-        e = r[:, 0] + (((r[:, 1] + r[:, 2]) + r[:, 3]) + r[:, 4])
-      h = np.flatnonzero(e < eps)
-      return int(h[0]) if h.size else -1
-
-    def last_sweep_sums(v, ns):          # v[0..15] <- the sums of sweep ns of a fused pass
-      if ns > 1:
-        v = v.copy()
-        v[:16] = v[20 + 16 * (ns - 2):36 + 16 * (ns - 2)]
-      return v
+    first_hit = lambda v, ns: _first_hit(v, ns, eps)
+    last_sweep_sums = _last_sweep_sums
 
     def d_pass(src, dst, ns, slot):
       for R in ranks:
