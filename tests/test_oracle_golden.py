@@ -68,3 +68,17 @@ def test_algorithm_failed_path_matches_reference():
   assert info["sol_nan"] and res[0][1] is None
   tried = [s for _, s in info["stepsz_tried"]]
   assert tried[1:] == d["stepsz_decrements"].tolist()
+
+
+def test_oracle_run_of_cfg3_blocks_equals_reference_run():
+  """BASELINE configs[2], time blocks 0-2 (11 104 iterations incl. three NaN fallbacks): the oracle's run
+  (scripts/make_oracle_golden.py) against the run of the reference's own sources through the shim (oracle/make_golden_baseline.py,
+  6.6 h of CPU).  Both fixtures are committed; every field they share must be identical, bit for bit."""
+  import os
+  gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+  ref = np.load(os.path.join(gdir, "baseline_cfg3_blocks012.npz"))
+  orc = np.load(os.path.join(gdir, "oracle_cfg3_blocks012.npz"))
+  assert ref["block_iters"].tolist() == [3810, 3704, 3590]                      # BASELINE.md / SURVEY App. C
+  assert ref["stepsz_used"].tolist() == [0.1, 0.07000000000000002, 0.07000000000000002]
+  for k in ("block_iters", "stepsz_used", "stepsz_decrements", "phi", "rho_sub", "alp_sub", "nt", "T", "sub"):
+    assert np.array_equal(ref[k], orc[k]), k
